@@ -1,0 +1,291 @@
+"""Host-side planner for the streaming aggregation kernel (csrc/aggregate.cu).
+
+Mirrors the coefficient stage of FedavgServer._aggregate (/root/reference/src/server/fedavgserver.py:
+601-653) in Python — bookkeeping stays on the host, bit-exact — and turns the accumulation stage
+(:656-666) plus upload()'s aux merge (/root/reference/src/client/fedavgclient.py:158-184) into one
+kernel launch over flat arenas:  every (global model, parameter) pair of the round is an *output*, every
+client tensor with a non-zero coefficient in at least one output is read exactly once.
+"""
+import re
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .arena import MatSpec
+
+MAX_OUT = 4
+LERP, WSUM = 0, 1
+SRC_PLAIN, SRC_HOLD, SRC_MERGE = 0, 1, 2
+
+
+# ---- name bookkeeping (fedavgserver.py:94-115, 183-238) ---------------------------------------------
+def get_name_type(name):
+    if "embeddings" in name:
+        return "embedding"
+    if "attention" in name or "attn" in name:
+        return "attn"
+    if "blocks" in name:
+        return "blocks"
+    if "mlp" in name:
+        return "mlp"
+    return "task"
+
+
+_num = re.compile(r"\d+")
+
+
+def get_first_number(s):
+    m = _num.search(s)
+    return int(m.group()) if m else None
+
+
+def get_name_modality(name, modalities):
+    i = get_first_number(name)
+    return modalities[i] if i is not None else None
+
+
+def init_param_scope(names, shared_param, share_scope):
+    target = {"none": None, "attn": "attn", "blocks": "blocks", "mlp": "mlp"}[shared_param]
+    return {n: (share_scope if target is not None and get_name_type(n) == target else "dataset") for n in names}
+
+
+@dataclass
+class GlobalCtx:
+    dataset: str
+    modality: str
+    task: str
+    out_modality_scale: float
+    spec: MatSpec
+    arena_in: torch.Tensor          # old global (flat fp32)
+    arena_out: torch.Tensor         # new global (may be the same tensor)
+
+
+@dataclass
+class ClientCtx:
+    id: int
+    dataset: str
+    modality: str
+    task: str
+    size: int
+    spec: MatSpec
+    arena: Optional[torch.Tensor]   # None for clients held by another rank (they only enter the normalisers)
+
+
+def _client_coefs(scope, pm, g: GlobalCtx, clients: List[ClientCtx], modalities, share_scope_flag, compensation,
+                  fedavg):
+    """{client id: python float} for one (global, scope, param-modality) class — fedavgserver.py:601-653."""
+    sizes = {c.id: c.size for c in clients}
+    byid = {c.id: c for c in clients}
+    num = {}
+    old_sum = sum(sizes.values())
+    for c in clients:
+        n = c.size
+        if scope == "all":
+            num[c.id] = n
+        elif scope == "dataset":
+            num[c.id] = n if c.dataset == g.dataset else 0
+        elif scope == "task":
+            num[c.id] = n if c.task == g.task else 0
+        elif scope == "modality":
+            if fedavg:
+                num[c.id] = n if c.modality == g.modality else 0
+            else:
+                num[c.id] = n if (c.modality in g.modality or g.modality in c.modality) else 0
+        elif scope == "modality_exact":
+            if fedavg:
+                continue       # the reference's fedavg=True branch has no modality_exact case
+            num[c.id] = n if (c.modality == pm or pm in c.modality) else 0
+        if not fedavg and c.modality != g.modality and g.out_modality_scale != 1:
+            old_sum -= num[c.id]
+            num[c.id] *= g.out_modality_scale
+            old_sum += num[c.id]
+    if compensation and not fedavg:
+        if share_scope_flag == "all":
+            return {k: float(v / old_sum) for k, v in num.items()}
+        if share_scope_flag == "modality" or (share_scope_flag == "modality_exact" and not pm):
+            comp = sum(s for i, s in sizes.items()
+                       if byid[i].modality in g.modality or g.modality in byid[i].modality)
+        elif share_scope_flag == "modality_exact":
+            last = clients[-1]        # stale loop variable `identifier` of the reference (:648), reproduced
+            comp = sum(s for i, s in sizes.items() if byid[i].modality == pm or pm in last.modality)
+        else:
+            raise KeyError("--compensation needs share_scope in {all, modality, modality_exact} "
+                           "(the reference leaves coefficients unset otherwise, fedavgserver.py:640-651)")
+        return {k: float(v / comp) if comp != 0 else 0 for k, v in num.items()}
+    tot = sum(num.values())
+    return {k: float(v / tot) if tot != 0 else 0 for k, v in num.items()}
+
+
+def upload_keys(spec: MatSpec, with_aux_flag: bool, modality: str):
+    """Keys present in FedavgClient.upload() (fedavgclient.py:158-184) and, per key, the aux partner."""
+    merged = with_aux_flag and modality != "img+txt"
+    out = {}
+    names = spec.aux_layer_names() if merged else ()
+    for s in spec.segments:
+        k = s.key
+        if merged and ("aux" in k or "cross_modal_scale" in k):
+            continue
+        aux = None
+        if merged and any(n in k for n in names) and "weight" in k:
+            ak, sk = k.replace("weight", "aux_weight"), k.replace("weight", "cross_modal_scale")
+            if ak in spec._by_key:
+                aux = (spec.seg(ak).offset, spec.seg(sk).offset)
+            else:
+                raise KeyError(ak)    # the reference raises the same KeyError (aux_*_only mismatch)
+        out[k] = (s.offset, s.numel, aux)
+    return out
+
+
+class AggregationPlan:
+    """Tables for one fc_aggregate launch (see include/fedcola_b200.h)."""
+
+    def __init__(self, globals_: List[GlobalCtx], clients: List[ClientCtx], param_scope: Dict[str, str],
+                 args_modalities, share_scope_flag, compensation, with_aux, mode=LERP, fedavg=False,
+                 include_global_term=True):
+        clients = sorted(clients, key=lambda c: c.id)
+        self.mode = mode
+        tile = int(_lib.lib().fc_aggregate_tile_floats())
+        coef_cache = {}
+        ukeys = {c.id: upload_keys(c.spec, with_aux, c.modality) for c in clients}
+        if mode == LERP and any(c.arena is None for c in clients):
+            raise ValueError("sequential-lerp aggregation needs every sampled client's arena on this GPU; "
+                             "use mode=WSUM for clients sharded across ranks")
+
+        # union of output parameter names, in first-seen order
+        names, outs = [], {}
+        for gi, g in enumerate(globals_):
+            for k in g.spec.required_keys():
+                kk = (k, g.spec.seg(k).numel)     # same name, different shape (vocab / classes) = separate jobs
+                if kk not in outs:
+                    outs[kk] = []
+                    names.append(kk)
+                outs[kk].append(gi)
+
+        job_numel, job_nout, job_gin, job_gout, job_gscale = [], [], [], [], []
+        job_src_start, src_ptr, src_flag, scale_ptr, coef = [0], [], [], [], []
+        self.job_names = []
+        self.algorithmic_bytes = 0
+        for name, numel in names:
+            glist = outs[(name, numel)]
+            for g0 in range(0, len(glist), MAX_OUT):
+                gs = glist[g0:g0 + MAX_OUT]
+                cs = []
+                for gi in gs:
+                    g = globals_[gi]
+                    scope = param_scope[name]
+                    pm = None if fedavg else get_name_modality(name, args_modalities)
+                    ck = (gi, scope, pm if (scope == "modality_exact" or
+                                            (compensation and share_scope_flag == "modality_exact")) else None)
+                    if ck not in coef_cache:
+                        coef_cache[ck] = _client_coefs(scope, pm, g, clients, args_modalities, share_scope_flag,
+                                                       compensation, fedavg)
+                    cs.append(coef_cache[ck])
+                rows = []
+                for c in clients:
+                    if name not in ukeys[c.id]:
+                        continue
+                    off, n, aux = ukeys[c.id][name]
+                    if n != numel:
+                        continue      # e.g. word embeddings of a different vocabulary: load_state_dict would raise
+                    cvals = [np.float32(cc[c.id]) for cc in cs]
+                    if not any(v != 0 for v in cvals):
+                        continue
+                    rows.append((c, off, aux, cvals))
+                if mode == WSUM and rows:
+                    # closed form of the sequential lerp, fp64 on the host:
+                    #   f = g*prod(1-c_k) + sum_k c_k*prod_{j>k}(1-c_j)*l_k
+                    C = np.asarray([[float(v) for v in r[3]] for r in rows], dtype=np.float64)   # [R, nout]
+                    one_minus = 1.0 - C
+                    suffix = np.ones_like(C)
+                    suffix[:-1] = np.cumprod(one_minus[::-1], axis=0)[::-1][1:]
+                    W = C * suffix
+                    wg = np.prod(one_minus, axis=0)
+                    rows = [(c, off, aux, [np.float32(x) for x in W[r]]) for r, (c, off, aux, _) in enumerate(rows)]
+                    gsc = [np.float32(x) if include_global_term else np.float32(0) for x in wg]
+                elif mode == WSUM:
+                    gsc = [np.float32(1.0 if include_global_term else 0.0)] * len(gs)
+                else:
+                    gsc = [np.float32(0)] * len(gs)
+                rows = [r for r in rows if r[0].arena is not None]     # remote clients only shape the weights
+                self.job_names.append(name)
+                job_numel.append(numel)
+                job_nout.append(len(gs))
+                for o in range(MAX_OUT):
+                    if o < len(gs):
+                        g = globals_[gs[o]]
+                        off = g.spec.seg(name).offset * 4
+                        job_gin.append(g.arena_in.data_ptr() + off)
+                        job_gout.append(g.arena_out.data_ptr() + off)
+                        job_gscale.append(gsc[o])
+                    else:
+                        job_gin.append(0), job_gout.append(0), job_gscale.append(np.float32(0))
+                for c, off, aux, cvals in rows:
+                    base = c.arena.data_ptr()
+                    cpad = cvals + [np.float32(0)] * (MAX_OUT - len(cvals))
+                    if aux:      # upload() hands the server W + A*s: a HOLD entry (W) then a MERGE entry (A, s)
+                        src_ptr.append(base + off * 4), src_flag.append(SRC_HOLD), scale_ptr.append(0)
+                        coef.extend([np.float32(0)] * MAX_OUT)
+                        src_ptr.append(base + aux[0] * 4), src_flag.append(SRC_MERGE)
+                        scale_ptr.append(base + aux[1] * 4)
+                        coef.extend(cpad)
+                    else:
+                        src_ptr.append(base + off * 4), src_flag.append(SRC_PLAIN), scale_ptr.append(0)
+                        coef.extend(cpad)
+                    self.algorithmic_bytes += 4 * numel * (2 if aux else 1)
+                job_src_start.append(len(src_ptr))
+                self.algorithmic_bytes += 4 * numel * 2 * len(gs)
+        tiles = [(n + tile - 1) // tile for n in job_numel]
+        self.n_jobs = len(job_numel)
+        self.n_tiles = int(sum(tiles))
+        self.host = dict(
+            job_tile_start=np.concatenate([[0], np.cumsum(tiles)]).astype(np.int32),
+            job_numel=np.asarray(job_numel, dtype=np.int64),
+            job_nout=np.asarray(job_nout, dtype=np.int32),
+            job_gin=np.asarray(job_gin, dtype=np.uint64),
+            job_gout=np.asarray(job_gout, dtype=np.uint64),
+            job_gscale=np.asarray(job_gscale, dtype=np.float32),
+            job_src_start=np.asarray(job_src_start, dtype=np.int32),
+            src_ptr=np.asarray(src_ptr, dtype=np.uint64),
+            src_flag=np.asarray(src_flag, dtype=np.int32),
+            scale_ptr=np.asarray(scale_ptr, dtype=np.uint64),
+            coef=np.asarray(coef, dtype=np.float32).reshape(-1),
+        )
+        self.dev = None
+        self._keep = (globals_, clients)
+
+    def to_device(self, device):
+        """Pack all tables into ONE pinned host buffer and copy once."""
+        order = ["job_tile_start", "job_numel", "job_nout", "job_gin", "job_gout", "job_gscale", "job_src_start",
+                 "src_ptr", "src_flag", "scale_ptr", "coef"]
+        offs, total = {}, 0
+        for k in order:
+            a = self.host[k]
+            total = (total + 15) // 16 * 16
+            offs[k] = total
+            total += max(a.nbytes, 16)
+        buf = np.zeros(total, dtype=np.uint8)
+        for k in order:
+            a = self.host[k]
+            buf[offs[k]:offs[k] + a.nbytes] = a.view(np.uint8).reshape(-1)
+        t = torch.from_numpy(buf)
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        self._dev_buf = t.to(device, non_blocking=True)
+        base = self._dev_buf.data_ptr()
+        self.dev = {k: base + offs[k] for k in order}
+        self.device = torch.device(device)
+        return self
+
+    def launch(self, grid_ctas=0):
+        if self.dev is None:
+            raise RuntimeError("AggregationPlan.to_device() must be called before launch()")
+        L, d, vp = _lib.lib(), self.dev, _lib.c_vp
+        rc = L.fc_aggregate(self.mode, self.n_jobs, self.n_tiles, vp(d["job_tile_start"]), vp(d["job_numel"]),
+                            vp(d["job_nout"]), vp(d["job_gin"]), vp(d["job_gout"]), vp(d["job_gscale"]),
+                            vp(d["job_src_start"]), vp(d["src_ptr"]), vp(d["src_flag"]), vp(d["scale_ptr"]),
+                            vp(d["coef"]), int(grid_ctas), self.device.index or 0,
+                            _lib.stream_ptr(self.device))
+        _lib.check(rc, "fc_aggregate")

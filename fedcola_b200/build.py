@@ -1,0 +1,71 @@
+"""Builds libfedcola_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "libfedcola_b200.so")
+STAMP = os.path.join(HERE, "csrc", ".build_stamp")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("FC_PTXAS_V") else "-O3",
+         "-I", os.path.join(ROOT, "include")]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files.append(os.path.join(ROOT, "include", "fedcola_b200.h"))
+    for f in files:
+        h.update(f.encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into one shared library. Returns the library path."""
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC}; cannot build libfedcola_b200.so")
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[fedcola_b200.build] {os.path.basename(src)} FAILED\n{out}\n")
+        elif verbose and out.strip():
+            sys.stderr.write(f"[fedcola_b200.build] {os.path.basename(src)}\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-Xlinker", "--no-as-needed"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

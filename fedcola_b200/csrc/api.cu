@@ -1,0 +1,8 @@
+// Library-wide entry points of libfedcola_b200.so.
+#include "common.cuh"
+#include "../../include/fedcola_b200.h"
+
+thread_local char fc_last_error_buf[512] = {0};
+
+extern "C" const char* fc_last_error(void) { return fc_last_error_buf; }
+extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }

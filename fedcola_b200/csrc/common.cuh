@@ -1,0 +1,72 @@
+// Shared helpers for the fedcola_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define FC_OK 0
+#define FC_ERR_INVALID (-1)
+#define FC_ERR_CUDA (-2)
+#define FC_ERR_UNSUPPORTED (-3)
+
+// Last error text, per thread (entry points are called from the reference's ThreadPoolExecutor workers).
+extern thread_local char fc_last_error_buf[512];
+
+#define FC_FAIL(code, ...)                                              \
+  do {                                                                  \
+    snprintf(fc_last_error_buf, sizeof(fc_last_error_buf), __VA_ARGS__); \
+    return (code);                                                      \
+  } while (0)
+
+#define FC_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      FC_FAIL(FC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define FC_LAUNCH_CHECK() FC_CUDA_CHECK(cudaGetLastError())
+
+#define FC_REQUIRE(cond, ...) \
+  do {                        \
+    if (!(cond)) FC_FAIL(FC_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+static inline int fc_num_sms(int device) {
+  static thread_local int cached_dev = -1, cached = 0;
+  if (cached_dev != device) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device);
+    cached_dev = device;
+  }
+  return cached > 0 ? cached : 148;
+}
+
+struct FcDeviceGuard {
+  int prev;
+  explicit FcDeviceGuard(int dev) { cudaGetDevice(&prev); if (dev >= 0 && dev != prev) cudaSetDevice(dev); else prev = -1; }
+  ~FcDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// 128-bit streaming loads/stores that bypass L1 (data touched once).
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
