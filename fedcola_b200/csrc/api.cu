@@ -6,3 +6,7 @@ thread_local char fc_last_error_buf[512] = {0};
 
 extern "C" const char* fc_last_error(void) { return fc_last_error_buf; }
 extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }
+
+// Struct-layout handshake for FFI bindings (ctypes / cgo stubs assert these at load time).
+extern "C" int fc_sizeof_mat_desc(void) { return (int)sizeof(fc_mat_desc); }
+extern "C" int fc_sizeof_step_args(void) { return (int)sizeof(fc_step_args); }

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, float* __restrict__ dx,
                                                      long long dx_row_stride, int accumulate,
-                                                     __nv_bfloat16* __restrict__ dxs, const float* __restrict__ row_scale,
+                                                     __nv_bfloat16* __restrict__ dxs, long long dxs_row_stride,
+                                                     const float* __restrict__ row_scale,
                                                      int rows_per_group, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, int rows, int d) {
   extern __shared__ float s_part[];   // [2][warps_per_block][d]
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
         }
         *dxr = o;
         if (dxs)
-          reinterpret_cast<uint2*>(dxs + (size_t)row * d)[c] =
+          reinterpret_cast<uint2*>(dxs + (size_t)row * dxs_row_stride)[c] =
               make_uint2(pack2(o.x * sc, o.y * sc), pack2(o.z * sc, o.w * sc));
       }
     }
@@ -188,8 +189,8 @@ extern "C" int fc_layernorm_fwd(const float* x, long long x_row_stride, const fl
 extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row_stride, const float* x,
                                 long long x_row_stride, const float* mean, const float* rstd, const float* gamma,
                                 float* dx, long long dx_row_stride, int accumulate, void* dxs_bf16,
-                                const float* row_scale, int rows_per_group, float* dgamma, float* dbeta, int rows,
-                                int d, int device, void* stream) {
+                                long long dxs_row_stride, const float* row_scale, int rows_per_group, float* dgamma,
+                                float* dbeta, int rows, int d, int device, void* stream) {
   FC_REQUIRE(rows >= 0 && d > 0 && d % 4 == 0 && d <= kMaxVec * 128, "fc_layernorm_bwd: d=%d unsupported", d);
   FC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "fc_layernorm_bwd: dgamma/dbeta must both be given");
   FC_REQUIRE(row_scale == nullptr || rows_per_group > 0, "fc_layernorm_bwd: rows_per_group");
@@ -208,12 +209,12 @@ extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row
   if (dy_is_bf16)
     ln_bwd_kernel<true><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx,
                                                       dx_row_stride, accumulate,
-                                                      reinterpret_cast<__nv_bfloat16*>(dxs_bf16), row_scale,
+                                                      reinterpret_cast<__nv_bfloat16*>(dxs_bf16), dxs_row_stride, row_scale,
                                                       rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, d);
   else
     ln_bwd_kernel<false><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx,
                                                        dx_row_stride, accumulate,
-                                                       reinterpret_cast<__nv_bfloat16*>(dxs_bf16), row_scale,
+                                                       reinterpret_cast<__nv_bfloat16*>(dxs_bf16), dxs_row_stride, row_scale,
                                                        rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, d);
   FC_LAUNCH_CHECK();
   return FC_OK;

@@ -31,3 +31,49 @@ def gemm_bf16(A, B, epi, out, *, a_mn=False, b_mn=False, out2=None, bias=None, r
                                  c_int(patches), c_f(alpha), c_int(splits), c_int(dev), _lib.stream_ptr(A.device))
     _lib.check(rc, "fc_gemm_bf16")
     return out
+
+
+def _st(t):
+    return _lib.stream_ptr(t.device)
+
+
+def attention_fwd(qkv, B, N, H, want_lse=True):
+    """qkv bf16 [B,N,3,H,64] -> (out bf16 [B,N,H*64], lse fp32 [B,H,N])"""
+    out = torch.empty(B, N, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device) if want_lse else None
+    rc = _lib.lib().fc_attention_fwd(ptr(qkv), ptr(out), ptr(lse), c_int(B), c_int(N), c_int(H), c_int(64),
+                                     c_int(_dev(qkv)), _st(qkv))
+    _lib.check(rc, "fc_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, B, N, H):
+    dqkv = torch.empty_like(qkv)
+    rc = _lib.lib().fc_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), c_int(B), c_int(N), c_int(H),
+                                     c_int(64), c_int(_dev(qkv)), _st(qkv))
+    _lib.check(rc, "fc_attention_bwd")
+    return dqkv
+
+
+def layernorm_fwd(x, gamma, beta, eps, bf16_out=True):
+    rows, d = x.shape
+    y = torch.empty(rows, d, dtype=torch.bfloat16 if bf16_out else torch.float32, device=x.device)
+    mean = torch.empty(rows, device=x.device)
+    rstd = torch.empty(rows, device=x.device)
+    rc = _lib.lib().fc_layernorm_fwd(ptr(x), c_ll(x.stride(0)), ptr(gamma), ptr(beta), c_f(eps),
+                                     ptr(y if bf16_out else None), ptr(None if bf16_out else y), ptr(mean), ptr(rstd),
+                                     c_int(rows), c_int(d), c_int(_dev(x)), _st(x))
+    _lib.check(rc, "fc_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dxs=None, row_scale=None, rows_per_group=0,
+                  dgamma=None, dbeta=None):
+    rows, d = x.shape
+    rc = _lib.lib().fc_layernorm_bwd(ptr(dy), c_int(int(dy.dtype == torch.bfloat16)), c_ll(dy.stride(0)), ptr(x),
+                                     c_ll(x.stride(0)), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), c_ll(dx.stride(0)),
+                                     c_int(int(accumulate)), ptr(dxs), c_ll(dxs.stride(0) if dxs is not None else d),
+                                     ptr(row_scale), c_int(rows_per_group), ptr(dgamma), ptr(dbeta), c_int(rows),
+                                     c_int(d), c_int(_dev(x)), _st(x))
+    _lib.check(rc, "fc_layernorm_bwd")
+    return dx

@@ -77,6 +77,161 @@ int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_maj
                  const void* aux, const float* pos, int patches, float alpha, int splits, int device,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused short-sequence attention (head_dim 64)        ref: src/models/mome.py:153-165 + autograd
+ *   qkv  bf16 [B, N, 3, H, 64]  (output of the qkv Linear, untouched layout)
+ *   out  bf16 [B, N, H*64]      lse fp32 [B, H, N] (row log-sum-exp of the scaled scores; may be NULL in fwd)
+ * ------------------------------------------------------------------------------------------------ */
+int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim, int device,
+                     void* stream);
+int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B,
+                     int N, int H, int head_dim, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the fp32 residual stream           ref: src/models/mome.py:203,215,226-227,751-752
+ *   fwd: y = LN(x) as bf16 (GEMM operand) and/or fp32; mean/rstd saved per row.
+ *   bwd: dx (+)= LN'(dy); optional bf16 copy dxs = row_scale[row/rows_per_group] * dx for the next
+ *        backward GEMM; dgamma/dbeta accumulated with atomics.
+ * ------------------------------------------------------------------------------------------------ */
+int fc_layernorm_fwd(const float* x, long long x_row_stride, const float* gamma, const float* beta, float eps,
+                     void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int d, int device,
+                     void* stream);
+int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row_stride, const float* x,
+                     long long x_row_stride, const float* mean, const float* rstd, const float* gamma,
+                     float* dx, long long dx_row_stride, int accumulate, void* dxs_bf16,
+                     long long dxs_row_stride, const float* row_scale, int rows_per_group, float* dgamma,
+                     float* dbeta, int rows, int d, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embeddings / heads / losses        ref: src/models/mome.py:597-611 (image), :632-639 (text, BertEmbeddings),
+ *   :641-659 (heads), src/client/fedavgclient.py:85-95 (CrossEntropyLoss / ContrastiveLoss)
+ * ------------------------------------------------------------------------------------------------ */
+int fc_im2col16(const float* img, void* patches_bf16, float* x, const float* cls_token, const float* pos_embed,
+                int B, int in_chans, int img_size, int d, int device, void* stream);
+int fc_patch_bwd_prep(const float* dx, void* dxp_bf16, float* dpos, float* dcls, float* dbias, int B, int patches,
+                      int d, int device, void* stream);
+int fc_text_embed_fwd(const long long* ids, const float* word, const float* pos, const float* type,
+                      const float* gamma, const float* beta, float eps, float* x, float* mean, float* rstd, int B,
+                      int L, int d, int device, void* stream);
+int fc_text_embed_bwd(const float* dx, const long long* ids, const float* word, const float* pos, const float* type,
+                      const float* gamma, const float* mean, const float* rstd, float* dword, float* dpos,
+                      float* dtype, float* dgamma, float* dbeta, int B, int L, int d, int device, void* stream);
+int fc_head_fwd(const float* feat, const float* W, const float* bias, float* logits, int B, int d, int C,
+                int device, void* stream);
+int fc_head_bwd(const float* dlogits, const float* feat, const float* W, float* dW, float* dbias, float* dfeat,
+                int B, int d, int C, int device, void* stream);
+/* loss_out[0] += mean CE; dlogits = d(mean CE)/dlogits * grad_scale; correct_out[0] += #(argmax == target) */
+int fc_ce_loss(const float* logits, const long long* target, float* dlogits, float* loss_out, float* correct_out,
+               int B, int C, float grad_scale, int device, void* stream);
+int fc_l2norm_fwd(const float* v, float* out, float* norm, int B, int d, int device, void* stream);
+int fc_l2norm_bwd(const float* dout, const float* out, const float* norm, float* dv, int B, int d, int device,
+                  void* stream);
+/* sim_ws: fp32 [B*B] workspace, lse_ws: fp32 [2*B] workspace */
+int fc_contrastive_loss(const float* a, const float* b, float* sim_ws, float* lse_ws, float* da, float* db,
+                        float* loss_out, int B, int d, float tau, float grad_scale, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Client optimizer step and friends     ref: src/client/fedavgclient.py:63,97-100 (AdamW/SGD, clip),
+ *   src/client/fedproxclient.py:64-67 (prox term), src/models/mome.py:58-60 (aux mix)
+ *   `chunks`: device array of {long long offset; int len; int segment;} work items (len <= fc_chunk_floats()).
+ *   grad_sumsq/max_norm: when max_norm > 0 the gradient is scaled by min(1, max_norm/(sqrt(*grad_sumsq)+1e-6)).
+ * ------------------------------------------------------------------------------------------------ */
+int fc_chunk_floats(void);
+int fc_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const void* chunks,
+                  int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  const float* grad_sumsq, float max_norm, int device, void* stream);
+int fc_sgd_step(float* params, const float* grads, float* momentum_buf, const void* chunks, int n_chunks, float lr,
+                float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                const float* grad_sumsq, float max_norm, int device, void* stream);
+/* out[segment] (or out[0] if single_output) += sum (a-b)^2 ; b may be NULL */
+int fc_sumsq(const float* a, const float* b, const void* chunks, int n_chunks, float* out, int single_output,
+             int device, void* stream);
+/* grads += mu*0.5*(p - pg)/||p - pg||_segment ; loss_out[0] += mu*0.5*sum_segments ||p - pg|| */
+int fc_prox_grad(float* grads, const float* params, const float* global_params, const void* chunks, int n_chunks,
+                 const float* seg_sumsq, int n_segments, float mu, float* loss_out, int device, void* stream);
+/* layers: device array of {long long w_off, a_off, s_off, dst_off, dstT_off; int rows, cols, tile_start;} */
+int fc_prep_weights(const float* params, void* operands_bf16, const void* layers, int n_layers, int n_tiles,
+                    int device, void* stream);
+/* layers: device array of {long long w_off, a_off, s_off, numel; int chunk_start; int pad;} */
+int fc_aux_grads(const float* params, float* grads, const void* layers, int n_layers, int n_chunks,
+                 int aux_trained, int device, void* stream);
+int fc_colsum_bf16(const void* x, long long ld, int rows, int n, float* out, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Native step driver                 ref: src/models/mome.py:881-922 (ModalityAgnosticTransformer.forward),
+ *   src/client/fedavgclient.py:79-102 and src/client/fedproxclient.py:64-71 (one batch of the update loop)
+ * ------------------------------------------------------------------------------------------------ */
+#define FC_MAX_DEPTH 24
+#define FC_MAX_SEGMENTS 2048
+#define FC_BLOCK_ROLES 20   /* n1w n1b qkvw qkvb qkvs qkva projw projb projs proja n2w n2b fc1w fc1b fc1s fc1a fc2w fc2b fc2s fc2a */
+
+typedef struct {
+  int d, depth, heads, hidden;          /* embed dim, #blocks, #heads (head_dim 64), mlp hidden */
+  int img_size, patches, in_chans;      /* 224, 196, 3|1 */
+  int seq_len, vocab, max_text_len;
+  int num_classes[2];                   /* per encoder slot (0 = img, 1 = txt); <= 0: retrieval / no head */
+  int has_enc[2];
+  int with_aux, aux_trained;
+  /* float offsets into the flat param arena (the grad / optimizer arenas share the layout); -1 = absent */
+  long long img_pos, img_cls, img_pw, img_pb;
+  long long txt_word, txt_pos, txt_type, txt_lnw, txt_lnb;
+  long long norm_w, norm_b;
+  long long head_w[2], head_b[2];
+  long long blk[2][FC_MAX_DEPTH][FC_BLOCK_ROLES];
+  /* bf16 element offsets into the operand arena: W_eff = W + s*A of every Linear, [out, in] row-major */
+  long long op_pw;
+  long long op[2][FC_MAX_DEPTH][4];     /* qkv, proj, fc1, fc2 */
+} fc_mat_desc;
+
+long long fc_mat_workspace_bytes(const fc_mat_desc* m, int B);
+/* out0/out1: logits fp32 [B, C] or (feat_out / retrieval) unit features fp32 [B, d]; NULL to skip the copy.
+ * droppath: fp32 [2 enc][depth][2 branches][B] per-sample scales (keep mask / keep prob) or NULL. */
+int fc_mat_forward(const fc_mat_desc* m, const float* params, const void* operands, void* workspace, int B,
+                   const float* img, const long long* ids, const float* droppath, int feat_out, float* out0,
+                   float* out1, int device, void* stream);
+/* Accumulates into grads (caller zeroes). dout0/dout1: gradient w.r.t. the forward outputs (NULL = none). */
+int fc_mat_backward(const fc_mat_desc* m, const float* params, const void* operands, void* workspace, int B,
+                    const long long* ids, const float* droppath, int feat_out, const float* dout0,
+                    const float* dout1, float* grads, const void* aux_layers, int n_aux_layers,
+                    int n_aux_chunks, int device, void* stream);
+
+#define FC_LOSS_CE_IMG 0
+#define FC_LOSS_CE_TXT 1
+#define FC_LOSS_CONTRASTIVE 2
+#define FC_OPT_NONE 0     /* forward + loss + backward only (gradients left in `grads`) */
+#define FC_OPT_ADAMW 1
+#define FC_OPT_SGD 2
+
+typedef struct {
+  int B;
+  int loss_kind, optimizer, step;       /* step: 1-based count since the optimizer was created */
+  float lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  int nesterov;
+  float max_grad_norm, prox_mu;
+  float* params;                        /* flat fp32 arena, updated in place */
+  float* grads;                         /* same layout; zeroed by the call */
+  float* opt_state0;                    /* AdamW exp_avg / SGD momentum buffer */
+  float* opt_state1;                    /* AdamW exp_avg_sq */
+  const float* global_params;           /* FedProx: frozen copy of the downloaded model */
+  void* operands;                       /* bf16 operand arena */
+  void* workspace;
+  long long arena_floats;
+  const float* img;                     /* fp32 [B, C, 224, 224] */
+  const long long* ids;                 /* int64 [B, seq_len] */
+  const long long* labels;              /* int64 [B] (CE) */
+  const float* droppath;
+  float* stats;                         /* [2]: += loss (incl. prox term), += #correct (CE only) */
+  const void* chunks; int n_chunks; int n_segments;      /* trainable chunk table */
+  const void* prep_layers; int n_prep_layers; int n_prep_tiles;
+  const void* aux_layers; int n_aux_layers; int n_aux_chunks;
+} fc_step_args;
+
+int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int device, void* stream);
+
+/* struct-layout handshake for FFI bindings */
+int fc_sizeof_mat_desc(void);
+int fc_sizeof_step_args(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -264,26 +264,11 @@ def image_embed(p, pre, img):                             # mome.py:597-611 + Pa
 def text_embed(p, pre, ids):                              # mome.py:632-639; HF BertEmbeddings, eps 1e-12
     L = ids.shape[1]
     t = pre + "text_embeddings."
-    x = p[t + "word_embeddings.weight"][ids] + p[t + "token_type_embeddings.weight"][0] \
+    # nn.Embedding(vocab, d, padding_idx=pad_token_id=0): row 0 is looked up normally but never gets gradient
+    x = F.embedding(ids, p[t + "word_embeddings.weight"], padding_idx=0) + p[t + "token_type_embeddings.weight"][0] \
         + p[t + "position_embeddings.weight"][:L]
     C = x.shape[-1]
     return F.layer_norm(x, (C,), p[t + "LayerNorm.weight"], p[t + "LayerNorm.bias"], 1e-12)
-
-
-def drop_path_masks(batch, depth, rate, training=True):
-    """Per-block (dp1, dp2) [B,1,1] scale tensors drawn from torch's global generator in the reference's
-    call order (timm DropPath: new_empty((B,1,1)).bernoulli_(keep).div_(keep)); None where rate==0."""
-    dpr = [x.item() for x in torch.linspace(0, rate, depth)]     # mome.py:726-728
-    out = []
-    for r in dpr:
-        if r > 0.0 and training:
-            keep = 1 - r
-            m1 = torch.empty((batch, 1, 1)).bernoulli_(keep).div_(keep)
-            m2 = torch.empty((batch, 1, 1)).bernoulli_(keep).div_(keep)
-            out.append((m1, m2))
-        else:
-            out.append((None, None))
-    return out
 
 
 def mat_forward(p, x, modalities, num_heads, depth, feat_out=False, drop_path_rate=0.0, training=True):
@@ -303,7 +288,6 @@ def mat_forward(p, x, modalities, num_heads, depth, feat_out=False, drop_path_ra
         if m is None:
             continue
         h = embeds[i]
-        dps = [(None, None)] * depth
         if drop_path_rate > 0 and training:
             # the reference draws inside each Block.forward → block j of encoder i: dp1 then dp2
             dpr = [v.item() for v in torch.linspace(0, drop_path_rate, depth)]
@@ -341,7 +325,6 @@ LOGIT_SCALE = math.log(1 / 0.07)
 
 def contrastive_loss(a, b):
     """torchmultimodal ContrastiveLossWithTemperature, fresh object every step → constant τ."""
-    t = math.exp(min(max(LOGIT_SCALE, 0.0), math.log(100)))
     lab = torch.arange(a.size(0))
     tt = torch.exp(torch.tensor(LOGIT_SCALE, dtype=torch.float32))
     return (F.cross_entropy(a @ b.t() * tt, lab) + F.cross_entropy(b @ a.t() * tt, lab)) / 2

@@ -144,3 +144,56 @@ def build_agg_case(name, device="cpu", seq_len=16):
     scope = agg.init_param_scope(names, sp, sc)
     mods = [DS_MODALITY[d] for d in datasets]
     return gl, cl, scope, dict(args_modalities=mods, share_scope_flag=sc, compensation=comp, with_aux=aux)
+
+
+# ---- training cases (shared by oracle tests, GPU parity tests and oracle/make_golden_train.py) -------------
+TRAIN_SEQ = 16
+TRAIN_KINDS = {
+    # name: (dataset, with_aux)
+    "img": ("CIFAR100", False),
+    "txt": ("AG_NEWS", False),
+    "pair": ("Flickr30k", False),
+    "img_aux": ("CIFAR100", True),
+    "txt_aux": ("AG_NEWS", True),
+}
+
+
+def make_samples(dataset, n, seed, seq_len=TRAIN_SEQ):
+    """Deterministic synthetic samples (numpy RandomState) in the reference's item layout."""
+    rng = np.random.RandomState(seed)
+    m = DS_MODALITY[dataset]
+    vocab = TINY_VOCAB.get(dataset, 512)
+    if m == "img":
+        return (torch.from_numpy(rng.standard_normal((n, 3, 224, 224)).astype(np.float32)),
+                torch.from_numpy(rng.randint(0, DS_CLASSES[dataset], size=n).astype(np.int64)))
+    if m == "txt":
+        return (torch.from_numpy(rng.randint(0, vocab, size=(n, seq_len)).astype(np.int64)),
+                torch.from_numpy(rng.randint(0, DS_CLASSES[dataset], size=n).astype(np.int64)))
+    return (torch.from_numpy(rng.standard_normal((n, 3, 224, 224)).astype(np.float32)),
+            torch.from_numpy(rng.randint(0, vocab, size=(n, seq_len)).astype(np.int64)))
+
+
+class TensorItems(torch.utils.data.Dataset):
+    """Wraps make_samples output as the reference's datasets do: (x, y) or (img, ids, i//5, i, i)."""
+
+    def __init__(self, dataset, n, seed, seq_len=TRAIN_SEQ):
+        self.modality = DS_MODALITY[dataset]
+        self.a, self.b = make_samples(dataset, n, seed, seq_len)
+
+    def __len__(self):
+        return self.a.shape[0]
+
+    def __getitem__(self, i):
+        if self.modality == "img+txt":
+            return self.a[i], self.b[i], i // 5, i, i
+        return self.a[i], self.b[i]
+
+
+def subsample(a, step=13):
+    return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])
+
+
+def train_spec(kind, drop_path_rate=0.0, size=TINY):
+    ds, aux = TRAIN_KINDS[kind]
+    return make_spec(ds, "attn", "modality", with_aux=aux, aux_trained=True, seq_len=TRAIN_SEQ, size=size,
+                     drop_path_rate=drop_path_rate)
