@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict
 // one block per sample. loss_out[0] += loss_b / B ; dlogits = (softmax - onehot) * gscale / B ; stats[0] += correct
 __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                                  float* __restrict__ dlogits, float* __restrict__ loss_out,
-                                                 float* __restrict__ correct_out, int B, int C, float gscale) {
+                                                 float* __restrict__ correct_out, float* __restrict__ loss_sum_out,
+                                                 int B, int C, float gscale) {
   __shared__ float s_red[33];
   __shared__ int s_arg;
   const int b = blockIdx.x;
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
       dlogits[(size_t)b * C + c] = (expf(z[c] - lse) - (c == t ? 1.0f : 0.0f)) * (gscale / B);
   if (threadIdx.x == 0) {
     atomicAdd(loss_out, (lse - z[t]) / B);
+    if (loss_sum_out != nullptr) atomicAdd(loss_sum_out, lse - z[t]);
     s_arg = C;
   }
   __syncthreads();
@@ -350,7 +352,8 @@ __global__ void __launch_bounds__(256) sim_kernel(const float* __restrict__ a, c
 }
 // pass 2: row / column log-sum-exp of S; loss += 0.5/B * ((lse_row_i - S_ii) + (lse_col_i - S_ii))
 __global__ void __launch_bounds__(128) lse_kernel(const float* __restrict__ S, float* __restrict__ lse_row,
-                                                  float* __restrict__ lse_col, float* __restrict__ loss_out, int B) {
+                                                  float* __restrict__ lse_col, float* __restrict__ loss_out,
+                                                  float* __restrict__ loss_sum_out, int B) {
   __shared__ float s_red[33];
   const int i = blockIdx.x;
   float mr = -INFINITY, mc = -INFINITY;
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(128) lse_kernel(const float* __restrict__ S, f
     lse_row[i] = lr;
     lse_col[i] = lc;
     atomicAdd(loss_out, 0.5f * ((lr - sii) + (lc - sii)) / B);
+    if (loss_sum_out != nullptr) atomicAdd(loss_sum_out, 0.5f * ((lr - sii) + (lc - sii)));
   }
 }
 // pass 3: G[i,j] = dL/dS[i,j] * tau = tau * gscale * 0.5/B * (softmax_row + softmax_col - 2*delta_ij);
@@ -494,11 +498,12 @@ extern "C" int fc_head_bwd(const float* dlogits, const float* feat, const float*
 }
 
 extern "C" int fc_ce_loss(const float* logits, const long long* target, float* dlogits, float* loss_out,
-                          float* correct_out, int B, int C, float grad_scale, int device, void* stream) {
+                          float* correct_out, float* loss_sum_out, int B, int C, float grad_scale, int device,
+                          void* stream) {
   if (B <= 0) return FC_OK;
   FcDeviceGuard guard(device);
-  ce_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, target, dlogits, loss_out, correct_out, B, C,
-                                                                 grad_scale);
+  ce_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, target, dlogits, loss_out, correct_out,
+                                                                 loss_sum_out, B, C, grad_scale);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -521,15 +526,15 @@ extern "C" int fc_l2norm_bwd(const float* dout, const float* out, const float* n
 }
 
 extern "C" int fc_contrastive_loss(const float* a, const float* b, float* sim_ws, float* lse_ws, float* da, float* db,
-                                   float* loss_out, int B, int d, float tau, float grad_scale, int device,
-                                   void* stream) {
+                                   float* loss_out, float* loss_sum_out, int B, int d, float tau, float grad_scale,
+                                   int device, void* stream) {
   FC_REQUIRE(d % 4 == 0 && B <= 4096, "fc_contrastive_loss: d %% 4, B <= 4096");
   if (B <= 0) return FC_OK;
   FcDeviceGuard guard(device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   sim_kernel<<<B, 256, 0, st>>>(a, b, sim_ws, B, d, tau);
   FC_LAUNCH_CHECK();
-  lse_kernel<<<B, 128, 0, st>>>(sim_ws, lse_ws, lse_ws + B, loss_out, B);
+  lse_kernel<<<B, 128, 0, st>>>(sim_ws, lse_ws, lse_ws + B, loss_out, loss_sum_out, B);
   FC_LAUNCH_CHECK();
   if (da != nullptr) {
     contrastive_grad_kernel<<<B, 128, sizeof(float) * 2 * B, st>>>(sim_ws, lse_ws, lse_ws + B, a, b, da, db, B, d,

@@ -338,7 +338,7 @@ extern "C" int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int d
   if (a->loss_kind == FC_LOSS_CONTRASTIVE) {
     FC_REQUIRE(m->has_enc[0] && m->has_enc[1], "contrastive loss needs both encoders");
     for (int e = 0; e < 2; ++e) TRY(fc_l2norm_fwd(w.enc[e].feat, w.enc[e].featn, w.enc[e].fnorm, B, d, device, stream));
-    TRY(fc_contrastive_loss(w.enc[0].featn, w.enc[1].featn, w.sim, w.lse_ws, w.da, w.db, a->stats, B, d,
+    TRY(fc_contrastive_loss(w.enc[0].featn, w.enc[1].featn, w.sim, w.lse_ws, w.da, w.db, a->stats, a->stats + 2, B, d,
                             1.0f / 0.07f, 1.0f, device, stream));
     TRY(fc_l2norm_bwd(w.da, w.enc[0].featn, w.enc[0].fnorm, w.enc[0].dfeat, B, d, device, stream));
     TRY(fc_l2norm_bwd(w.db, w.enc[1].featn, w.enc[1].fnorm, w.enc[1].dfeat, B, d, device, stream));
@@ -350,7 +350,7 @@ extern "C" int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int d
     EncWs& s = w.enc[e];
     const int C = m->num_classes[e];
     TRY(fc_head_fwd(s.feat, c.p(m->head_w[e]), c.p(m->head_b[e]), s.logits, B, d, C, device, stream));
-    TRY(fc_ce_loss(s.logits, a->labels, w.dlogits, a->stats, a->stats + 1, B, C, 1.0f, device, stream));
+    TRY(fc_ce_loss(s.logits, a->labels, w.dlogits, a->stats, a->stats + 1, a->stats + 2, B, C, 1.0f, device, stream));
     TRY(fc_head_bwd(w.dlogits, s.feat, c.p(m->head_w[e]), c.g(m->head_w[e]), c.g(m->head_b[e]), s.dfeat, B, d, C,
                     device, stream));
     TRY(encoder_backward(c, w, e, a->ids));
@@ -363,7 +363,7 @@ extern "C" int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int d
     FC_CUDA_CHECK(cudaMemsetAsync(w.seg_sumsq, 0, sizeof(float) * a->n_segments, st));
     TRY(fc_sumsq(a->params, a->global_params, a->chunks, a->n_chunks, w.seg_sumsq, 0, device, stream));
     TRY(fc_prox_grad(a->grads, a->params, a->global_params, a->chunks, a->n_chunks, w.seg_sumsq, a->n_segments,
-                     a->prox_mu, a->stats, device, stream));
+                     a->prox_mu, a->stats, a->stats + 2, (float)B, device, stream));
   }
   // ---- clip_grad_norm_ (fedavgclient.py:98-99): global L2 norm over the trainable tensors
   const float* sumsq = nullptr;

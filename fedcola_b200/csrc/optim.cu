@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) prox_grad_kernel(float* __restrict__ grad
 }
 
 // prox loss value: out[0] += mu*0.5*sum_seg sqrt(sumsq[seg])
-__global__ void prox_loss_kernel(const float* __restrict__ seg_sumsq, int n_seg, float mu, float* __restrict__ out) {
+__global__ void prox_loss_kernel(const float* __restrict__ seg_sumsq, int n_seg, float mu, float* __restrict__ out,
+                                 float* __restrict__ out_weighted, float weight) {
   float acc = 0.f;
   for (int i = threadIdx.x; i < n_seg; i += blockDim.x) acc += sqrtf(seg_sumsq[i]);
   acc = warp_sum(acc);
@@ -154,7 +155,10 @@ __global__ void prox_loss_kernel(const float* __restrict__ seg_sumsq, int n_seg,
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, 0.5f * mu * t);
+    if (threadIdx.x == 0) {
+      atomicAdd(out, 0.5f * mu * t);
+      if (out_weighted != nullptr) atomicAdd(out_weighted, 0.5f * mu * t * weight);
+    }
   }
 }
 
@@ -343,7 +347,7 @@ extern "C" int fc_sumsq(const float* a, const float* b, const void* chunks, int 
 
 extern "C" int fc_prox_grad(float* grads, const float* params, const float* global_params, const void* chunks,
                             int n_chunks, const float* seg_sumsq, int n_segments, float mu, float* loss_out,
-                            int device, void* stream) {
+                            float* loss_weighted_out, float weight, int device, void* stream) {
   if (n_chunks <= 0) return FC_OK;
   FcDeviceGuard guard(device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -352,7 +356,7 @@ extern "C" int fc_prox_grad(float* grads, const float* params, const float* glob
                                                                  seg_sumsq, mu);
   FC_LAUNCH_CHECK();
   if (loss_out != nullptr) {
-    prox_loss_kernel<<<1, 256, 0, st>>>(seg_sumsq, n_segments, mu, loss_out);
+    prox_loss_kernel<<<1, 256, 0, st>>>(seg_sumsq, n_segments, mu, loss_out, loss_weighted_out, weight);
     FC_LAUNCH_CHECK();
   }
   return FC_OK;

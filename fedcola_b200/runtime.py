@@ -341,7 +341,7 @@ class ClientTrainer:
         # fresh optimizer state every round, as the reference re-creates the optimizer (fedavgclient.py:63)
         self.state0 = torch.zeros_like(model.arena) if (self.opt == OPT_ADAMW or momentum != 0.0) else None
         self.state1 = torch.zeros_like(model.arena) if self.opt == OPT_ADAMW else None
-        self.stats = torch.zeros(2, dtype=torch.float32, device=rt.device)
+        self.stats = torch.zeros(4, dtype=torch.float32, device=rt.device)
         self.step_count = 0
         self.global_arena = global_arena
         a = StepArgs()

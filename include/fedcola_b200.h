@@ -120,15 +120,17 @@ int fc_head_fwd(const float* feat, const float* W, const float* bias, float* log
                 int device, void* stream);
 int fc_head_bwd(const float* dlogits, const float* feat, const float* W, float* dW, float* dbias, float* dfeat,
                 int B, int d, int C, int device, void* stream);
-/* loss_out[0] += mean CE; dlogits = d(mean CE)/dlogits * grad_scale; correct_out[0] += #(argmax == target) */
+/* loss_out[0] += mean CE; dlogits = d(mean CE)/dlogits * grad_scale; correct_out[0] += #(argmax == target);
+ * loss_sum_out[0] += sum of per-sample losses (what MetricManager.track accumulates: loss * len(batch)) */
 int fc_ce_loss(const float* logits, const long long* target, float* dlogits, float* loss_out, float* correct_out,
-               int B, int C, float grad_scale, int device, void* stream);
+               float* loss_sum_out, int B, int C, float grad_scale, int device, void* stream);
 int fc_l2norm_fwd(const float* v, float* out, float* norm, int B, int d, int device, void* stream);
 int fc_l2norm_bwd(const float* dout, const float* out, const float* norm, float* dv, int B, int d, int device,
                   void* stream);
 /* sim_ws: fp32 [B*B] workspace, lse_ws: fp32 [2*B] workspace */
 int fc_contrastive_loss(const float* a, const float* b, float* sim_ws, float* lse_ws, float* da, float* db,
-                        float* loss_out, int B, int d, float tau, float grad_scale, int device, void* stream);
+                        float* loss_out, float* loss_sum_out, int B, int d, float tau, float grad_scale, int device,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Client optimizer step and friends     ref: src/client/fedavgclient.py:63,97-100 (AdamW/SGD, clip),
@@ -146,9 +148,11 @@ int fc_sgd_step(float* params, const float* grads, float* momentum_buf, const vo
 /* out[segment] (or out[0] if single_output) += sum (a-b)^2 ; b may be NULL */
 int fc_sumsq(const float* a, const float* b, const void* chunks, int n_chunks, float* out, int single_output,
              int device, void* stream);
-/* grads += mu*0.5*(p - pg)/||p - pg||_segment ; loss_out[0] += mu*0.5*sum_segments ||p - pg|| */
+/* grads += mu*0.5*(p - pg)/||p - pg||_segment ; loss_out[0] += L, loss_weighted_out[0] += weight*L,
+ * L = mu*0.5*sum_segments ||p - pg|| */
 int fc_prox_grad(float* grads, const float* params, const float* global_params, const void* chunks, int n_chunks,
-                 const float* seg_sumsq, int n_segments, float mu, float* loss_out, int device, void* stream);
+                 const float* seg_sumsq, int n_segments, float mu, float* loss_out, float* loss_weighted_out,
+                 float weight, int device, void* stream);
 /* layers: device array of {long long w_off, a_off, s_off, dst_off, dstT_off; int rows, cols, tile_start;} */
 int fc_prep_weights(const float* params, void* operands_bf16, const void* layers, int n_layers, int n_tiles,
                     int device, void* stream);
@@ -220,7 +224,8 @@ typedef struct {
   const long long* ids;                 /* int64 [B, seq_len] */
   const long long* labels;              /* int64 [B] (CE) */
   const float* droppath;
-  float* stats;                         /* [2]: += loss (incl. prox term), += #correct (CE only) */
+  float* stats;                         /* [3]: += step loss (incl. prox term), += #correct (CE only),
+                                           += step loss * B (MetricManager's running loss) */
   const void* chunks; int n_chunks; int n_segments;      /* trainable chunk table */
   const void* prep_layers; int n_prep_layers; int n_prep_tiles;
   const void* aux_layers; int n_aux_layers; int n_aux_chunks;

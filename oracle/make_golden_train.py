@@ -99,6 +99,35 @@ UPDATE_RUNS = {
 }
 
 
+def ref_round(case):
+    """One full `FedavgServer.update()` / `FedproxServer.update()` of the unmodified reference."""
+    import random
+    import helpers as H
+    ref_shim.install()
+    import src.server.fedavgserver as fs
+    fs.VOCAB_SIZES.update(H.TINY_VOCAB)
+    args, cds, datasets = H.round_args(case)
+    random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    if args.algorithm == "fedprox":
+        from src.server.fedproxserver import FedproxServer as S
+    else:
+        S = fs.FedavgServer
+    server = S(args=args, writer=ref_shim.NullWriter(), server_dataset=(None, {}), client_datasets=cds,
+               model_str=args.model_name)
+    for i, ds in enumerate(datasets):
+        spec = H.round_global_spec(case, ds)
+        sd = {k: torch.from_numpy(v.copy()) for k, v in H.state_dict_of(spec, H.fill_arena(spec, 100 + i)).items()}
+        server.global_models[ds].load_state_dict(sd, strict=True)
+    server.round = 1
+    ids = server.update()
+    res = {"ids": np.asarray(ids), "loss_avg": np.float32(server.results[1]["clients_updated"]["loss"]["avg"])}
+    for ds in datasets:
+        for k, v in server.global_models[ds].state_dict().items():
+            res[f"{ds}:{k}"] = H.subsample(v.detach().numpy(), 7)
+    return res
+
+
 def main():
     import helpers as H
     ref_shim.install()
@@ -114,6 +143,10 @@ def main():
             for k, v in ref_update(kind, alg, opt, lr, mu, clip).items():
                 out[f"{kind}/{run}/{k}"] = v
         print("train", kind)
+    for case in H.ROUND_CASES:
+        for k, v in ref_round(case).items():
+            out[f"round/{case}/{k}"] = v
+        print("round", case)
     np.savez_compressed(os.path.join(GOLDEN, "train_golden.npz"), **out)
     print("bytes", os.path.getsize(os.path.join(GOLDEN, "train_golden.npz")))
 

@@ -197,3 +197,38 @@ def train_spec(kind, drop_path_rate=0.0, size=TINY):
     ds, aux = TRAIN_KINDS[kind]
     return make_spec(ds, "attn", "modality", with_aux=aux, aux_trained=True, seq_len=TRAIN_SEQ, size=size,
                      drop_path_rate=drop_path_rate)
+
+
+# ---- full-round cases ----------------------------------------------------------------------------------------
+ROUND_CASES = {
+    # name: dict(args overrides), clients [(dataset, n, seed)]
+    "fedavg": (dict(algorithm="fedavg", shared_param="none", share_scope="dataset"),
+               [("CIFAR100", 8, 51), ("AG_NEWS", 12, 52)], ["CIFAR100", "AG_NEWS"]),
+    "fedcola": (dict(algorithm="fedavg", shared_param="attn", share_scope="modality", compensation=True, with_aux=True,
+                     aux_trained=True),
+                [("CIFAR100", 8, 51), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)], ["CIFAR100", "AG_NEWS", "Flickr30k"]),
+    "fedprox": (dict(algorithm="fedprox", shared_param="none", share_scope="dataset", mu=0.1),
+                [("CIFAR100", 8, 51), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)], ["CIFAR100", "AG_NEWS", "Flickr30k"]),
+    "fediot": (dict(algorithm="fedavg", shared_param="blocks", share_scope="modality_exact"),
+               [("CIFAR100", 8, 51), ("CIFAR100", 4, 54), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)],
+               ["CIFAR100", "AG_NEWS", "Flickr30k"]),
+}
+
+
+def round_args(case):
+    from fedcola_b200.harness import make_args
+    over, clients, datasets = ROUND_CASES[case]
+    kw = dict(model_name="mome_d64_l2", datasets=list(datasets) + ["Coco"],
+              modalities=[DS_MODALITY[d] for d in datasets] + ["img+txt"], seq_len=TRAIN_SEQ, K=len(clients),
+              Ks=[1], Cs=[1.0], B=4, E=1, optimizer="SGD", lr=0.05, momentum=0.9, out_modality_scales=[1, 1, 1, 1],
+              dropout=0.0, no_shuffle=True, seed=1)
+    kw.update(over)
+    args = make_args(**kw)
+    cds = [(TensorItems(ds, n, seed), None, CLIENT_TASK[DS_MODALITY[ds]], DS_MODALITY[ds], ds) for ds, n, seed in clients]
+    return args, cds, datasets
+
+
+def round_global_spec(case, ds):
+    over, _, _ = ROUND_CASES[case]
+    return make_spec(ds, over.get("shared_param", "none"), over.get("share_scope", "dataset"),
+                     with_aux=over.get("with_aux", False), aux_trained=over.get("aux_trained", False), seq_len=TRAIN_SEQ)
