@@ -112,9 +112,11 @@ class FedavgClient(BaseClient):
         self.model.to(dev)
         if self.args.distributed or (self.args.mm_distributed and self.modality == "img+txt"):
             raise NotImplementedError("nn.DataParallel inside a client is replaced by client sharding across GPUs")
-        if self._staged is None or self._staged.device != dev:
-            self._staged = _StagedData(self.training_set, self.modality, getattr(self.args, "data_resident", "host"), dev)
-        data = self._staged
+        resident = getattr(self.args, "data_resident", "host")
+        cache = self.training_set.__dict__.setdefault("_fc_staged", {})     # shared by clients sharing a dataset
+        if (resident, str(dev)) not in cache:
+            cache[(resident, str(dev))] = _StagedData(self.training_set, self.modality, resident, dev)
+        data = self._staged = cache[(resident, str(dev))]
         with torch.cuda.device(dev):
             trainer = self.trainer = self._make_trainer()        # fresh optimizer state every round (:63)
             spec = self.model.spec

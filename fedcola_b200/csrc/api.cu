@@ -3,6 +3,9 @@
 #include "../../include/fedcola_b200.h"
 
 thread_local char fc_last_error_buf[512] = {0};
+unsigned long long fc_launch_counter = 0;
+
+extern "C" unsigned long long fc_launch_count(void) { return __atomic_load_n(&fc_launch_counter, __ATOMIC_RELAXED); }
 
 extern "C" const char* fc_last_error(void) { return fc_last_error_buf; }
 extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }

@@ -26,7 +26,13 @@ extern thread_local char fc_last_error_buf[512];
       FC_FAIL(FC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-#define FC_LAUNCH_CHECK() FC_CUDA_CHECK(cudaGetLastError())
+// Every kernel launch of the library goes through FC_LAUNCH_CHECK: it also feeds fc_launch_count().
+extern unsigned long long fc_launch_counter;
+#define FC_LAUNCH_CHECK()                                         \
+  do {                                                            \
+    __atomic_fetch_add(&fc_launch_counter, 1ULL, __ATOMIC_RELAXED); \
+    FC_CUDA_CHECK(cudaGetLastError());                            \
+  } while (0)
 
 #define FC_REQUIRE(cond, ...) \
   do {                        \

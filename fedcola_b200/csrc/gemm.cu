@@ -19,6 +19,7 @@
 #include "../../include/fedcola_b200.h"
 
 #include <mutex>
+#include <vector>
 
 namespace {
 
@@ -302,6 +303,12 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long cols, l
   return FC_OK;
 }
 
+// Optional per-launch timing (bench.py's roofline): CUDA events on the launching stream around every GEMM.
+struct ProfRec { cudaEvent_t a, b; double flops; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+int g_prof_on = 0;
+
 template <int A_MN, int B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
   auto kern = gemm_bf16_kernel<A_MN, B_MN>;
@@ -314,12 +321,46 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     configured_dev = dev;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+  ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K};
+  const bool prof = __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) != 0;
+  if (prof) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    cudaEventRecord(rec.a, st);
+  }
   kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  if (prof) {
+    cudaEventRecord(rec.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
 
 }  // namespace
+
+extern "C" void fc_gemm_profile(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  __atomic_store_n(&g_prof_on, enable, __ATOMIC_RELAXED);
+}
+
+// Sums the recorded launches (synchronises on their events). Returns the number of launches.
+extern "C" long long fc_gemm_profile_collect(double* total_ms, double* total_flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms += t;
+    fl += r.flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return (long long)g_prof.size();
+}
 
 extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
                             long long ldb, int b_mn_major, int epi, void* out, void* out2, long long ldo,

@@ -85,11 +85,16 @@ DATASET_MODALITY = {"CIFAR100": "img", "MedMNIST": "img", "AG_NEWS": "txt", "MTS
 DATASET_CLASSES = {"CIFAR100": 100, "AG_NEWS": 4, "MedMNIST": 11, "MTSamples": 40, "MedicalAbstracts": 5}
 
 
-def make_client_datasets(spec, seq_len=64):
+def make_client_datasets(spec, seq_len=64, share=False):
     """spec: list of (dataset_name, n_samples, seed) -> the reference's `client_datasets` list of
-    (train, test, task, modality, dataset_name) tuples (src/loaders/data.py:156,424)."""
-    out = []
+    (train, test, task, modality, dataset_name) tuples (src/loaders/data.py:156,424).
+    share=True: clients with the same (dataset, n) share one synthetic tensor set (benchmarks: dozens of
+    clients, only the sampled ones are ever touched)."""
+    out, cache = [], {}
     for name, n, seed in spec:
+        if share and (name, n) in cache:
+            out.append(cache[(name, n)])
+            continue
         mod = DATASET_MODALITY[name]
         vocab = DATASET_VOCAB.get(name, 30522)
         if mod == "img":
@@ -99,4 +104,5 @@ def make_client_datasets(spec, seq_len=64):
         else:
             ds, task = SyntheticPair(n, seq_len, vocab, seed), "img+txt"
         out.append((ds, None, task, mod, name))
+        cache[(name, n)] = out[-1]
     return out

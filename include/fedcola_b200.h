@@ -23,6 +23,8 @@ extern "C" {
 
 const char* fc_last_error(void);
 int fc_abi_version(void);
+/* number of CUDA kernels this library has launched so far in this process */
+unsigned long long fc_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Server aggregation                                    ref: src/server/fedavgserver.py:597,656-666
@@ -76,6 +78,10 @@ int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_maj
                  const float* bias, const float* resid, const float* row_scale, int rows_per_group,
                  const void* aux, const float* pos, int patches, float alpha, int splits, int device,
                  void* stream);
+
+/* Per-launch GEMM timing with CUDA events on the launching stream (measurement aid; off by default). */
+void fc_gemm_profile(int enable);
+long long fc_gemm_profile_collect(double* total_ms, double* total_flops);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused short-sequence attention (head_dim 64)        ref: src/models/mome.py:153-165 + autograd
