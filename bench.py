@@ -160,6 +160,18 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), samples, agg_ms, agg_bytes
 
+    if a.profile:      # ncu --profile-from-start off: one warm round, then ONE profiled round
+        server, args = make_server("device")
+        server.round += 1
+        server.update()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        server.round += 1
+        server.update()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     # ---- kernel-side number: client data resident in HBM ---------------------------------------------
     server, args = make_server("device")
     sampler = ClockSampler(local) if rank == 0 else None
@@ -305,6 +317,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

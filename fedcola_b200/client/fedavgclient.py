@@ -43,19 +43,22 @@ class _StagedData:
             self.cols.append(c)
         self.resident, self.device, self.n = resident, device, n
 
-    def batch(self, idx):
-        """idx: list[int] (from the DataLoader's own batch sampler) -> device tensors."""
+    def open(self):
+        """Device view of the data for one update(): the HBM-resident tensors, or (host-resident) one async
+        host->device copy of the client's set from pinned memory on the current stream — batches are then
+        gathered on the GPU instead of being fancy-indexed by the CPU."""
+        if self.resident == "device":
+            return self.cols
+        return [c.to(self.device, non_blocking=True) for c in self.cols]
+
+    @staticmethod
+    def batch(dev_cols, idx):
+        """idx: list[int] (from the DataLoader's own batch sampler) -> contiguous device tensors."""
         contiguous = len(idx) > 0 and idx == list(range(idx[0], idx[0] + len(idx)))
-        out = []
-        for c in self.cols:
-            if contiguous:
-                b = c[idx[0]:idx[0] + len(idx)]
-            else:
-                b = c[torch.as_tensor(idx, device=c.device)]
-            if not b.is_cuda:
-                b = b.to(self.device, non_blocking=True)
-            out.append(b.contiguous())
-        return out
+        if contiguous:
+            return [c[idx[0]:idx[0] + len(idx)] for c in dev_cols]
+        ix = torch.as_tensor(idx, device=dev_cols[0].device)
+        return [c.index_select(0, ix) for c in dev_cols]
 
 
 class FedavgClient(BaseClient):
@@ -123,6 +126,7 @@ class FedavgClient(BaseClient):
             kind = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}[self.modality]
             rng_mode = getattr(self.args, "droppath_rng", "fused")
             results = {}
+            dev_cols = data.open()
             logger.info(f"[{self.task.upper()}] [{self.modality.upper()}] ...working on client {self.id}... ")
             for e in range(self.args.E):
                 trainer.stats.zero_()
@@ -130,7 +134,7 @@ class FedavgClient(BaseClient):
                 for idx in self.train_loader.batch_sampler:     # same sampler => same shuffling RNG as the reference
                     if num >= 2 and self.args.debug:
                         break
-                    a, b = data.batch(idx)
+                    a, b = data.batch(dev_cols, idx)
                     dp = R.droppath_scales(spec, len(idx), dev, True, rng_mode)
                     if self.modality == "img":
                         trainer.step(a, None, b, kind, dp)
@@ -148,6 +152,7 @@ class FedavgClient(BaseClient):
                 results[e + 1] = res
                 logger.info(f"[Client {self.id}] loss: {res['loss']}" +
                             (f", acc1: {res['metrics'].get('acc1')}" if self.modality != "img+txt" else ""))
+            del dev_cols
         return results
 
     @torch.inference_mode()

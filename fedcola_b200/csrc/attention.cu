@@ -318,7 +318,7 @@ template <int NPAD>
 int launch_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int N, int H, float scale,
                cudaStream_t st) {
   const int smem = 3 * NPAD * LDS * 2;
-  FC_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FC_SMEM_OPT_IN(attn_fwd_kernel<NPAD>, smem);
   attn_fwd_kernel<NPAD><<<B * H, 128, smem, st>>>(qkv, out, lse, N, H, scale);
   FC_LAUNCH_CHECK();
   return FC_OK;
@@ -327,7 +327,7 @@ template <int NPAD>
 int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse,
                __nv_bfloat16* dqkv, int B, int N, int H, float scale, cudaStream_t st) {
   const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4;
-  FC_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FC_SMEM_OPT_IN(attn_bwd_kernel<NPAD>, smem);
   attn_bwd_kernel<NPAD><<<B * H, 256, smem, st>>>(qkv, o, dout, lse, dqkv, N, H, scale);
   FC_LAUNCH_CHECK();
   return FC_OK;

@@ -48,6 +48,20 @@ static inline int fc_num_sms(int device) {
   return cached > 0 ? cached : 148;
 }
 
+// Opt a kernel into > 48 KB of dynamic shared memory once per (thread, device) instead of on every launch.
+#define FC_SMEM_OPT_IN(kernel, bytes)                                                             \
+  do {                                                                                            \
+    static thread_local int _cfg_dev = -1;                                                        \
+    static thread_local int _cfg_bytes = 0;                                                       \
+    int _dev = -1;                                                                                \
+    cudaGetDevice(&_dev);                                                                         \
+    if (_dev != _cfg_dev || (int)(bytes) > _cfg_bytes) {                                          \
+      FC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _cfg_dev = _dev;                                                                            \
+      _cfg_bytes = (int)(bytes);                                                                  \
+    }                                                                                             \
+  } while (0)
+
 struct FcDeviceGuard {
   int prev;
   explicit FcDeviceGuard(int dev) { cudaGetDevice(&prev); if (dev >= 0 && dev != prev) cudaSetDevice(dev); else prev = -1; }

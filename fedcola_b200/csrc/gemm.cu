@@ -6,11 +6,13 @@
 //   bias, exact-erf GELU (fwd + derivative), DropPath-scaled residual add, patch-row remap + pos_embed,
 //   split-K gradient accumulation.
 //
-// One CTA = one 128 x 128 output tile (UMMA M=128, N=128, K=16 per instruction), 3-stage TMA->smem ring
-// of 64-wide K blocks (128-byte swizzle), accumulator in 128 TMEM columns; 6 warps: TMA producer, MMA
-// issuer (+TMEM alloc), 4 epilogue warps (one TMEM lane quarter each).  ~97 KB smem => two CTAs per SM,
-// so one CTA's epilogue overlaps the other's main loop (these GEMMs have K = 384..1536: short main
-// loops, store-heavy epilogues).
+// Persistent, warp-specialised kernel: one CTA per SM walks 128 x BN output tiles (BN = 128 / 192 / 256,
+// UMMA M=128, N=BN, K=16 per instruction).  A 4-6 stage TMA->smem ring of 64-wide K blocks (128-byte
+// swizzle) runs across tile boundaries; the fp32 accumulator is double-buffered in TMEM (2 x 256 columns)
+// so the 4 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
+// K = 384..1536: short main loops, store-heavy epilogues.  The epilogue transposes each 32x32 accumulator
+// block through shared memory so that every global load/store of a warp covers whole 64/128-byte row
+// segments (resid / pre-activation reads and all writes are coalesced).
 //
 // Operand majors: A and B may each be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows
 // contiguous) — the latter serves dW = dY^T X without materialising any transpose.
@@ -25,14 +27,24 @@ namespace {
 
 using namespace sm100;
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int STAGE_LD = 36;               // floats per row of the epilogue transpose buffer (144 B: conflict-free)
+constexpr int EPI_STAGE_BYTES = 4 * 32 * STAGE_LD * 4;
+constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
+
+template <int BN> struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
   int M, N, K;              // output rows, output cols, reduction length
-  int kb_per_split;         // K blocks handled by one blockIdx.z
+  int kb_per_split, splits; // K blocks handled by one split; number of splits
+  int m_tiles, n_tiles;
   int epi;
   int ldo;                  // leading dimension (elements) of out/out2/resid/aux
   void* out;
@@ -61,119 +73,78 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// One thread owns one output row and 32 consecutive columns [col0, col0+32).
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, float (&acc)[32]) {
-  if (row >= p.M || col0 >= p.N) return;
-  const int ncol = min(32, p.N - col0);        // N is a multiple of 8
+// Epilogue on 4 consecutive columns of one output row.  8 lanes cover 32 columns of a row, so every global
+// access of a warp touches 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.
+__device__ __forceinline__ void epilogue_vec4(const GemmParams& p, int row, int col, float4 a) {
+  if (row >= p.M || col >= p.N) return;        // N is a multiple of 8, col a multiple of 4
   if (p.bias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (i < ncol) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-        acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
-      }
-    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   }
-  const size_t o = static_cast<size_t>(row) * p.ldo + col0;
+  const size_t o = static_cast<size_t>(row) * p.ldo + col;
   switch (p.epi) {
-    case FC_EPI_BF16: {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        if (i < ncol)
-          dst[i / 8] = make_uint4(pack_bf16(acc[i], acc[i + 1]), pack_bf16(acc[i + 2], acc[i + 3]),
-                                  pack_bf16(acc[i + 4], acc[i + 5]), pack_bf16(acc[i + 6], acc[i + 7]));
-    } break;
-    case FC_EPI_GELU: {
-      uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-      uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o);
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        if (i < ncol) {
-          d1[i / 8] = make_uint4(pack_bf16(acc[i], acc[i + 1]), pack_bf16(acc[i + 2], acc[i + 3]),
-                                 pack_bf16(acc[i + 4], acc[i + 5]), pack_bf16(acc[i + 6], acc[i + 7]));
-          float g[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = gelu_erf(acc[i + j]);
-          d2[i / 8] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]),
-                                 pack_bf16(g[6], g[7]));
-        }
-    } break;
+    case FC_EPI_BF16:
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+      break;
+    case FC_EPI_GELU:
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o) =
+          make_uint2(pack_bf16(gelu_erf(a.x), gelu_erf(a.y)), pack_bf16(gelu_erf(a.z), gelu_erf(a.w)));
+      break;
     case FC_EPI_RESID: {
       const float s = p.row_scale ? __ldg(p.row_scale + row / p.rows_per_group) : 1.0f;
-      const float4* r = reinterpret_cast<const float4*>(p.resid + o);
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (i < ncol) {
-          const float4 x = r[i / 4];
-          dst[i / 4] = make_float4(x.x + s * acc[i], x.y + s * acc[i + 1], x.z + s * acc[i + 2], x.w + s * acc[i + 3]);
-        }
+      const float4 x = *reinterpret_cast<const float4*>(p.resid + o);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
+          make_float4(x.x + s * a.x, x.y + s * a.y, x.z + s * a.z, x.w + s * a.w);
     } break;
     case FC_EPI_DGELU: {
-      const uint4* pre = reinterpret_cast<const uint4*>(p.aux + o);
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        if (i < ncol) {
-          const uint4 q = pre[i / 8];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-          float g[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 x = __bfloat1622float2(h[j]);
-            g[2 * j] = acc[i + 2 * j] * gelu_erf_grad(x.x);
-            g[2 * j + 1] = acc[i + 2 * j + 1] * gelu_erf_grad(x.y);
-          }
-          dst[i / 8] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]),
-                                  pack_bf16(g[6], g[7]));
-        }
+      const uint2 q = *reinterpret_cast<const uint2*>(p.aux + o);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) =
+          make_uint2(pack_bf16(a.x * gelu_erf_grad(lo.x), a.y * gelu_erf_grad(lo.y)),
+                     pack_bf16(a.z * gelu_erf_grad(hi.x), a.w * gelu_erf_grad(hi.y)));
     } break;
-    case FC_EPI_F32: {
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (i < ncol) dst[i / 4] = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-    } break;
-    case FC_EPI_ATOMIC_F32: {
-      float* dst = reinterpret_cast<float*>(p.out) + o;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (i < ncol)
-          red_add_v4(dst + i, p.alpha * acc[i], p.alpha * acc[i + 1], p.alpha * acc[i + 2], p.alpha * acc[i + 3]);
-    } break;
+    case FC_EPI_F32:
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = a;
+      break;
+    case FC_EPI_ATOMIC_F32:
+      red_add_v4(reinterpret_cast<float*>(p.out) + o, p.alpha * a.x, p.alpha * a.y, p.alpha * a.z, p.alpha * a.w);
+      break;
     case FC_EPI_PATCH: {
       // row = b*P + t  ->  token row b*(P+1) + 1 + t of x; add pos_embed[1+t]
       const int b = row / p.patches, t = row - b * p.patches;
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                              (static_cast<size_t>(b) * (p.patches + 1) + 1 + t) * p.ldo + col0);
-      const float4* pe = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col0);
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (i < ncol) {
-          const float4 e = __ldg(pe + i / 4);
-          dst[i / 4] = make_float4(acc[i] + e.x, acc[i + 1] + e.y, acc[i + 2] + e.z, acc[i + 3] + e.w);
-        }
+      const float4 e = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                 (static_cast<size_t>(b) * (p.patches + 1) + 1 + t) * p.ldo + col) =
+          make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
     } break;
     default: break;
   }
 }
 
-template <int A_MN, int B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+// Persistent, warp-specialised: each CTA (one per SM) walks tiles  t = blockIdx.x, +gridDim.x, ...
+//   tile -> (split, m_blk, n_blk), n fastest so CTAs running side by side share the A rows in L2.
+// smem ring (TMA -> MMA) runs across tile boundaries; the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -185,11 +156,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full_bar[b], 1);
+        mbar_init(&tmem_empty_bar[b], 4);            // one arrival per epilogue warp
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -197,40 +171,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (kb1 > kb0) {
-    if (warp == 0) {
-      if (lane == 0) {
-        int s = 0;
-        uint32_t ph = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn, mn = tile - split * tiles_mn;
+        const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          uint8_t* a_dst = smem + s * C::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          if (A_MN) {   // [K, M] global: box {64 (m), 64 (k)} x2
+          if (A_MN) {   // [K, M] global: boxes {64 (m), 64 (k)}
             tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
             tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
           } else {      // [M, K] global: box {64 (k), 128 (m)}
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
           }
           if (B_MN) {
-            tma_load_2d(b_dst, &tmB, &full_bar[s], n0, kb * BK);
-            tma_load_2d(b_dst + 8192, &tmB, &full_bar[s], n0 + 64, kb * BK);
-          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+          } else {      // box {64 (k), BN (n)}
             tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-        int s = 0;
-        uint32_t ph = 0;
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_COLS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -240,32 +226,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                      : umma_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(tmem_full_bar);            // accumulator complete
+        umma_commit(&tmem_full_bar[buf]);      // accumulator complete
       }
-    } else {
-      const int q = warp & 3;                  // TMEM lane quarter this warp may access
-      mbar_wait(tmem_full_bar, 0);
+    }
+  } else {
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    float* stage = epi_stage + q * (32 * STAGE_LD);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mn = tile % tiles_mn;
+      const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;                // warp-uniform
         float acc[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+        tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
-        epilogue_chunk(p, row, n0 + c * 32, acc);
+        if (c == BN / 32 - 1 || col0 + 32 >= p.N) {   // last TMEM read of this tile: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        // transpose through smem: thread = row  ->  8 lanes per row, 4 columns each
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j * 4) =
+              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 4 * i;
+          const float4 v = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + c4);
+          epilogue_vec4(p, m0 + q * 32 + r, col0 + c4, v);
+        }
+        __syncwarp();
       }
-      tc_fence_before();
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -309,18 +321,13 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 int g_prof_on = 0;
 
-template <int A_MN, int B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
-  auto kern = gemm_bf16_kernel<A_MN, B_MN>;
-  // the >48 KB dynamic-smem opt-in is per device; remember which device this thread last configured
-  static thread_local int configured_dev = -1;
-  int dev = -1;
-  cudaGetDevice(&dev);
-  if (dev != configured_dev) {
-    FC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured_dev = dev;
-  }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+template <int BN, int A_MN, int B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device, cudaStream_t st) {
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  FC_SMEM_OPT_IN(kern, Cfg<BN>::SMEM_BYTES);
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  int grid = fc_num_sms(device);
+  if (grid > total_tiles) grid = total_tiles;
   ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K};
   const bool prof = __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) != 0;
   if (prof) {
@@ -328,7 +335,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     cudaEventCreate(&rec.b);
     cudaEventRecord(rec.a, st);
   }
-  kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
   if (prof) {
     cudaEventRecord(rec.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -336,6 +343,31 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   }
   FC_LAUNCH_CHECK();
   return FC_OK;
+}
+
+template <int BN>
+int launch_majors(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int a_mn, int b_mn, int device,
+                  cudaStream_t st) {
+  if (a_mn && b_mn) return launch<BN, 1, 1>(ta, tb, p, device, st);
+  if (a_mn) return launch<BN, 1, 0>(ta, tb, p, device, st);
+  if (b_mn) return launch<BN, 0, 1>(ta, tb, p, device, st);
+  return launch<BN, 0, 0>(ta, tb, p, device, st);
+}
+
+// Tile width: minimise (waves over the SMs) x (per-tile cost ~ BN + fixed overhead), i.e. trade the better
+// operand reuse of wide tiles against wave quantisation and zero-padded columns.
+int pick_bn(int M, int N, int splits, int sms) {
+  const int cands[3] = {256, 192, 128};
+  int best = 128;
+  double best_cost = 1e30;
+  const int m_tiles = (M + BM - 1) / BM;
+  for (int bn : cands) {
+    const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn) * splits;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double cost = (double)waves * (bn + 96.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -378,13 +410,34 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   FC_REQUIRE(row_scale == nullptr || rows_per_group > 0, "fc_gemm_bf16: rows_per_group");
   FcDeviceGuard guard(device);
   const int total_kb = (K + BK - 1) / BK;
+  const int sms = fc_num_sms(device);
+  int bn = 0;
+  if (splits <= 0 && epi == FC_EPI_ATOMIC_F32) {
+    // auto split-K: (tile width, #splits) minimising  waves x (main loop + atomic epilogue) over the SMs
+    double best = 1e30;
+    const int cands[3] = {256, 192, 128};
+    const int max_s = total_kb / 2 > 1 ? (total_kb / 2 < 64 ? total_kb / 2 : 64) : 1;
+    for (int c : cands) {
+      const long long base = (long long)((M + BM - 1) / BM) * ((N + c - 1) / c);
+      for (int sp = 1; sp <= max_s; ++sp) {
+        const int per = (total_kb + sp - 1) / sp;
+        const long long tiles = base * ((total_kb + per - 1) / per);
+        const long long waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (per * (c + 64.0) + 2.0 * c + 200.0);
+        if (cost < best - 1e-9) { best = cost; bn = c; splits = sp; }
+      }
+    }
+  }
   if (splits < 1) splits = 1;
   if (splits > total_kb) splits = total_kb;
   FC_REQUIRE(splits == 1 || epi == FC_EPI_ATOMIC_F32, "fc_gemm_bf16: split-K needs the atomic epilogue");
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.kb_per_split = (total_kb + splits - 1) / splits;
-  splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (bn == 0) bn = pick_bn(M, N, p.splits, sms);
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + bn - 1) / bn;
   p.epi = epi; p.ldo = static_cast<int>(ldo);
   p.out = out; p.out2 = out2; p.bias = bias; p.resid = resid; p.row_scale = row_scale;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
@@ -394,11 +447,10 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   // K-major operand: global [rows, K]; MN-major operand: global [K, rows].
   rc = a_mn_major ? make_tmap(&ta, A, K, M, lda, 64, 64) : make_tmap(&ta, A, M, K, lda, 64, BM);
   if (rc) return rc;
-  rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, BN);
+  rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, bn);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a_mn_major && b_mn_major) return launch<1, 1>(ta, tb, p, splits, st);
-  if (a_mn_major) return launch<1, 0>(ta, tb, p, splits, st);
-  if (b_mn_major) return launch<0, 1>(ta, tb, p, splits, st);
-  return launch<0, 0>(ta, tb, p, splits, st);
+  if (bn == 256) return launch_majors<256>(ta, tb, p, a_mn_major, b_mn_major, device, st);
+  if (bn == 192) return launch_majors<192>(ta, tb, p, a_mn_major, b_mn_major, device, st);
+  return launch_majors<128>(ta, tb, p, a_mn_major, b_mn_major, device, st);
 }

@@ -9,7 +9,7 @@
 
 namespace {
 
-constexpr int kMaxVec = 8;   // float4 per lane -> d <= 1024
+constexpr int kMaxVec = 8;   // float4 per lane -> d <= 1024 (kernels are instantiated for NV = 1,2,3,4,6,8)
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -17,6 +17,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // ---- forward -----------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, long long x_row_stride,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, __nv_bfloat16* __restrict__ y_bf16,
@@ -27,10 +28,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const int nvec = d >> 2;
   for (int row = warp; row < rows; row += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_row_stride);
-    float4 v[kMaxVec];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
         v[i] = xr[c];
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float mean = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
         const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
       if (rstd_out) rstd_out[row] = rstd;
     }
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // ---- backward ----------------------------------------------------------------------------------
 // dx_row = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (x-mean)*rstd
 // DY_BF16: dy is bf16 (output of a backward GEMM) else fp32.
-template <bool DY_BF16>
+template <int NV, bool DY_BF16>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, long long dy_row_stride,
                                                      const float* __restrict__ x, long long x_row_stride,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -87,17 +88,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int warp = blockIdx.x * wpb + wib, nwarps = gridDim.x * wpb;
   const int nvec = d >> 2;
-  float4 dg[kMaxVec], db[kMaxVec];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int row = warp; row < rows; row += nwarps) {
     const float m = mean[row], r = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_row_stride);
-    float4 g[kMaxVec], xh[kMaxVec];
+    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
         float4 dyv;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
     const float sc = row_scale ? __ldg(row_scale + row / rows_per_group) : 1.0f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
         float4 o;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   float* pg = s_part;
   float* pb = s_part + wpb * d;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
       reinterpret_cast<float4*>(pg + wib * d)[c] = dg[i];
@@ -180,8 +181,13 @@ extern "C" int fc_layernorm_fwd(const float* x, long long x_row_stride, const fl
   int grid = (rows + wpb - 1) / wpb;
   const int cap = fc_num_sms(device) * 8;
   if (grid > cap) grid = cap;
-  ln_fwd_kernel<<<grid, wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, x_row_stride, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define FC_LN_FWD(NV) ln_fwd_kernel<NV><<<grid, wpb * 32, 0, st>>>(x, x_row_stride, gamma, beta, eps, yb, y_f32, mean, rstd, rows, d)
+  const int nv = (d + 127) / 128;
+  if (nv <= 1) FC_LN_FWD(1); else if (nv == 2) FC_LN_FWD(2); else if (nv == 3) FC_LN_FWD(3);
+  else if (nv == 4) FC_LN_FWD(4); else if (nv <= 6) FC_LN_FWD(6); else FC_LN_FWD(8);
+#undef FC_LN_FWD
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -198,24 +204,30 @@ extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row
   FcDeviceGuard guard(device);
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
-  const int cap = fc_num_sms(device) * 2;     // few, fat CTAs: one atomicAdd per column per CTA
+  const int cap = fc_num_sms(device) * 4;     // 4 CTAs/SM; one atomicAdd per column per CTA for dgamma/dbeta
   if (grid > cap) grid = cap;
   const size_t smem = dgamma ? sizeof(float) * 2 * wpb * d : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (smem > 48 * 1024) {
-    FC_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FC_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  if (dy_is_bf16)
-    ln_bwd_kernel<true><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx,
-                                                      dx_row_stride, accumulate,
-                                                      reinterpret_cast<__nv_bfloat16*>(dxs_bf16), dxs_row_stride, row_scale,
-                                                      rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, d);
-  else
-    ln_bwd_kernel<false><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx,
-                                                       dx_row_stride, accumulate,
-                                                       reinterpret_cast<__nv_bfloat16*>(dxs_bf16), dxs_row_stride, row_scale,
-                                                       rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, d);
+  auto dxs = reinterpret_cast<__nv_bfloat16*>(dxs_bf16);
+  const int rpg = rows_per_group > 0 ? rows_per_group : 1;
+#define FC_LN_BWD(NV)                                                                                              \
+  do {                                                                                                             \
+    if (dy_is_bf16) {                                                                                              \
+      if (smem > 48 * 1024) FC_SMEM_OPT_IN((ln_bwd_kernel<NV, true>), smem);                                       \
+      ln_bwd_kernel<NV, true><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx, \
+                                                           dx_row_stride, accumulate, dxs, dxs_row_stride, row_scale, \
+                                                           rpg, dgamma, dbeta, rows, d);                           \
+    } else {                                                                                                       \
+      if (smem > 48 * 1024) FC_SMEM_OPT_IN((ln_bwd_kernel<NV, false>), smem);                                      \
+      ln_bwd_kernel<NV, false><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx, \
+                                                            dx_row_stride, accumulate, dxs, dxs_row_stride, row_scale, \
+                                                            rpg, dgamma, dbeta, rows, d);                          \
+    }                                                                                                              \
+  } while (0)
+  const int nv = (d + 127) / 128;
+  if (nv <= 1) FC_LN_BWD(1); else if (nv == 2) FC_LN_BWD(2); else if (nv == 3) FC_LN_BWD(3);
+  else if (nv == 4) FC_LN_BWD(4); else if (nv <= 6) FC_LN_BWD(6); else FC_LN_BWD(8);
+#undef FC_LN_BWD
   FC_LAUNCH_CHECK();
   return FC_OK;
 }

@@ -139,13 +139,8 @@ int gemm(const Ctx& c, int M, int N, int K, const void* A, long long lda, int a_
 
 // dW[rows_out, cols_out] += dY[T, rows_out]^T X[T, cols_out]   (both operands MN-major, split-K over tokens)
 int gemm_dw(const Ctx& c, int rows_out, int cols_out, int T, const void* dY, const void* X, float* dW) {
-  const int tiles = ((rows_out + 127) / 128) * ((cols_out + 127) / 128);
-  const int kb = (T + 63) / 64;
-  int splits = (2 * fc_num_sms(c.device) + tiles - 1) / tiles;
-  if (splits > kb / 4) splits = kb / 4;
-  if (splits < 1) splits = 1;
   return gemm(c, rows_out, cols_out, T, dY, rows_out, 1, X, cols_out, 1, FC_EPI_ATOMIC_F32, dW, nullptr, cols_out,
-              nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, splits);
+              nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, /*splits: auto*/ 0);
 }
 
 int encoder_forward(const Ctx& c, Ws& w, int e, const float* img, const long long* ids) {

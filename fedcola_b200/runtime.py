@@ -120,20 +120,27 @@ class ModelPlan:
         self.chunk = chunk
 
     def chunk_table(self, requires_grad):
-        """Work items over the trainable segments. requires_grad: {key: bool}. Returns (table, n_segments)."""
-        rows, seg_id = [], 0
-        for s in self.spec.unique_segments():
-            if not requires_grad.get(s.key, s.requires_grad):
-                continue
-            for o in range(0, s.numel, self.chunk):
-                rows.append((s.offset + o, min(self.chunk, s.numel - o), seg_id))
-            seg_id += 1
-        if seg_id > MAX_SEGMENTS:
+        """Work items over the trainable segments. requires_grad: {key: bool}. Returns (table, n_segments).
+        Vectorised and cached per requires_grad signature (a ViT-S client has ~21k chunks)."""
+        segs = [s for s in self.spec.unique_segments() if requires_grad.get(s.key, s.requires_grad)]
+        sig = tuple(s.key for s in segs)
+        cache = self.__dict__.setdefault("_chunk_cache", {})
+        if sig in cache:
+            return cache[sig]
+        if len(segs) > MAX_SEGMENTS:
             raise ValueError("too many parameter tensors")
-        t = np.zeros(len(rows), dtype=CHUNK_DT)
-        for i, r in enumerate(rows):
-            t[i] = r
-        return t, seg_id
+        offs = np.asarray([s.offset for s in segs], dtype=np.int64)
+        nums = np.asarray([s.numel for s in segs], dtype=np.int64)
+        per = (nums + self.chunk - 1) // self.chunk
+        seg_id = np.repeat(np.arange(len(segs), dtype=np.int64), per)
+        first = np.concatenate([[0], np.cumsum(per)[:-1]])
+        k = np.arange(int(per.sum()), dtype=np.int64) - np.repeat(first, per)      # chunk index inside its segment
+        t = np.zeros(len(k), dtype=CHUNK_DT)
+        t["off"] = offs[seg_id] + k * self.chunk
+        t["len"] = np.minimum(self.chunk, nums[seg_id] - k * self.chunk)
+        t["seg"] = seg_id
+        cache[sig] = (t, len(segs))
+        return cache[sig]
 
     def workspace_bytes(self, B):
         n = _lib.lib().fc_mat_workspace_bytes(ctypes.byref(self.desc), int(B))
@@ -163,19 +170,36 @@ def _to_dev(np_table, device):
     return t.to(device)
 
 
+_PLAN_CACHE = {}
+
+
+def plan_for(spec: MatSpec) -> ModelPlan:
+    """ModelPlans are static per architecture: cache them (a round creates one runtime per sampled client)."""
+    sig = (spec.embed_dim, spec.depth, spec.num_heads, spec.modalities, spec.num_classes, spec.tasks, spec.vocab_size,
+           spec.max_text_len, spec.img_size, spec.patch_size, spec.in_chans, spec.mlp_ratio, spec.with_aux,
+           spec.aux_trained, spec.aux_attn_only, spec.aux_mlp_only, spec.share_scope, tuple(spec.keys()))
+    p = _PLAN_CACHE.get(sig)
+    if p is None:
+        p = _PLAN_CACHE[sig] = ModelPlan(spec)
+    return p
+
+
 class ModelRuntime:
     """Device buffers of one model instance: bf16 operand arena, workspace, grad arena, tables."""
 
     def __init__(self, spec: MatSpec, arena: torch.Tensor):
         _lib.require_cuda(arena, "model arena")
         _sigs()
-        self.plan = ModelPlan(spec)
+        self.plan = plan_for(spec)
         self.arena = arena
         self.device = arena.device
         self.dev_index = arena.device.index if arena.device.index is not None else torch.cuda.current_device()
         self.operands = torch.zeros(self.plan.operand_elems, dtype=torch.bfloat16, device=self.device)
-        self.prep_dev = _to_dev(self.plan.prep_table, self.device)
-        self.aux_dev = _to_dev(self.plan.aux_table, self.device)
+        dev_tables = self.plan.__dict__.setdefault("_dev_tables", {})
+        if str(self.device) not in dev_tables:
+            dev_tables[str(self.device)] = (_to_dev(self.plan.prep_table, self.device),
+                                            _to_dev(self.plan.aux_table, self.device))
+        self.prep_dev, self.aux_dev = dev_tables[str(self.device)]
         self.workspace, self.ws_batch = None, 0
         self.grads = None
         self.operands_version = None
@@ -336,7 +360,11 @@ class ClientTrainer:
         flags = {k: p.requires_grad for k, p in model._params_by_key.items()}
         table, nseg = rt.plan.chunk_table(flags)
         self.n_chunks, self.n_segments = len(table), nseg
-        self.chunks_dev = _to_dev(table, rt.device)
+        cdev = rt.plan.__dict__.setdefault("_chunk_dev", {})
+        ck = (id(table), str(rt.device))
+        if ck not in cdev:
+            cdev[ck] = _to_dev(table, rt.device)
+        self.chunks_dev = cdev[ck]
         self.grads = rt.ensure_grads()
         # fresh optimizer state every round, as the reference re-creates the optimizer (fedavgclient.py:63)
         self.state0 = torch.zeros_like(model.arena) if (self.opt == OPT_ADAMW or momentum != 0.0) else None

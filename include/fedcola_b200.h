@@ -70,7 +70,7 @@ int fc_aggregate(int mode, int n_jobs, int n_tiles, const int* job_tile_start,
 #define FC_EPI_RESID 2       /* out(f32)  = resid + row_scale[row/rows_per_group] * (acc + bias)    */
 #define FC_EPI_DGELU 3       /* out(bf16) = acc * gelu_erf'(aux)     (aux = bf16 pre-activation)    */
 #define FC_EPI_F32 4         /* out(f32)  = acc + bias                                              */
-#define FC_EPI_ATOMIC_F32 5  /* out(f32) += alpha * acc  (red.add; split-K over blockIdx.z)         */
+#define FC_EPI_ATOMIC_F32 5  /* out(f32) += alpha * acc  (red.add; split-K; splits <= 0 = choose automatically) */
 #define FC_EPI_PATCH 6       /* out(f32)[b*(P+1)+1+t] = acc + bias + pos[1+t]  (row = b*P + t)      */
 
 int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
