@@ -9,7 +9,7 @@
 // Persistent, warp-specialised kernel: one CTA per SM walks 128 x BN output tiles (BN = 128 / 192 / 256,
 // UMMA M=128, N=BN, K=16 per instruction).  A 4-6 stage TMA->smem ring of 64-wide K blocks (128-byte
 // swizzle) runs across tile boundaries; the fp32 accumulator is double-buffered in TMEM (2 x 256 columns)
-// so the 4 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
+// so the 8 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
 // K = 384..1536: short main loops, store-heavy epilogues.  The epilogue transposes each 32x32 accumulator
 // block through shared memory so that every global load/store of a warp covers whole 64/128-byte row
 // segments (resid / pre-activation reads and all writes are coalesced).
@@ -29,15 +29,16 @@ using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 constexpr int STAGE_LD = 36;               // floats per row of the epilogue transpose buffer (144 B: conflict-free)
-constexpr int EPI_STAGE_BYTES = 4 * 32 * STAGE_LD * 4;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
 template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -59,11 +60,30 @@ struct GemmParams {
   float alpha;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU() default) evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf
+// (|error| <= 1.5e-7, far below the bf16 rounding of the stored result): one MUFU.RCP + one MUFU.EX2 + 6 FMAs
+// instead of erff's ~30-instruction polynomial — the GELU epilogues are ALU-bound otherwise.
+//   Phi(x) = 0.5*(1 + erf(x/sqrt2));  with z = |x|/sqrt2, t = 1/(1 + p z):  1 - erf(z) = poly(t) * exp(-z^2)
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  e = __expf(-z * z);                                             // = exp(-x^2/2), shared with the pdf term
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float tail = 0.5f * t * poly * e;                         // = 0.5*(1 - erf(z)) = Phi(-|x|), no cancellation
+  cdf = x >= 0.0f ? 1.0f - tail : tail;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);               // Phi(x) + x*phi(x)
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -73,54 +93,118 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Epilogue on 4 consecutive columns of one output row.  8 lanes cover 32 columns of a row, so every global
-// access of a warp touches 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.
-__device__ __forceinline__ void epilogue_vec4(const GemmParams& p, int row, int col, float4 a) {
-  if (row >= p.M || col >= p.N) return;        // N is a multiple of 8, col a multiple of 4
-  if (p.bias != nullptr) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+// Epilogue of one 32x32 accumulator block that sits transposed in `stage` (row-major, STAGE_LD floats per
+// row).  Lane l owns columns col..col+3 (col = col0 + 4*(l&7)) of rows r_i = (l>>3) + 4*i, i = 0..7: every
+// global access of the warp covers 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.  All global LOADS
+// of a block are issued before the first dependent use, so their latency is paid once per block.
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const float* stage, int row_base, int col0, int lane) {
+  const int rsub = lane >> 3, col = col0 + (lane & 7) * 4;
+  if (col >= p.N) return;                       // N is a multiple of 8, col a multiple of 4
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(stage + (rsub + 4 * i) * STAGE_LD + (lane & 7) * 4);
+    v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w;
   }
-  const size_t o = static_cast<size_t>(row) * p.ldo + col;
+  const int r0 = row_base + rsub;
+#define ROW(i) (r0 + 4 * (i))
+#define OFF(i) (static_cast<size_t>(ROW(i)) * p.ldo + col)
   switch (p.epi) {
-    case FC_EPI_BF16:
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
-      break;
-    case FC_EPI_GELU:
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o) =
-          make_uint2(pack_bf16(gelu_erf(a.x), gelu_erf(a.y)), pack_bf16(gelu_erf(a.z), gelu_erf(a.w)));
-      break;
+    case FC_EPI_BF16: {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M)
+          *reinterpret_cast<uint2*>(out + OFF(i)) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    } break;
+    case FC_EPI_GELU: {
+      __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out);
+      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M) {
+          *reinterpret_cast<uint2*>(o1 + OFF(i)) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+          *reinterpret_cast<uint2*>(o2 + OFF(i)) = make_uint2(pack_bf16(gelu_erf(v[i].x), gelu_erf(v[i].y)),
+                                                              pack_bf16(gelu_erf(v[i].z), gelu_erf(v[i].w)));
+        }
+    } break;
     case FC_EPI_RESID: {
-      const float s = p.row_scale ? __ldg(p.row_scale + row / p.rows_per_group) : 1.0f;
-      const float4 x = *reinterpret_cast<const float4*>(p.resid + o);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
-          make_float4(x.x + s * a.x, x.y + s * a.y, x.z + s * a.z, x.w + s * a.w);
+      float4 x[8];
+      float sc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[i] = 1.0f;
+        if (ROW(i) < p.M) {
+          x[i] = *reinterpret_cast<const float4*>(p.resid + OFF(i));
+          if (p.row_scale) sc[i] = __ldg(p.row_scale + ROW(i) / p.rows_per_group);
+        }
+      }
+      float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M)
+          *reinterpret_cast<float4*>(out + OFF(i)) = make_float4(x[i].x + sc[i] * v[i].x, x[i].y + sc[i] * v[i].y,
+                                                                 x[i].z + sc[i] * v[i].z, x[i].w + sc[i] * v[i].w);
     } break;
     case FC_EPI_DGELU: {
-      const uint2 q = *reinterpret_cast<const uint2*>(p.aux + o);
-      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
-      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) =
-          make_uint2(pack_bf16(a.x * gelu_erf_grad(lo.x), a.y * gelu_erf_grad(lo.y)),
-                     pack_bf16(a.z * gelu_erf_grad(hi.x), a.w * gelu_erf_grad(hi.y)));
+      uint2 q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        q[i] = make_uint2(0u, 0u);
+        if (ROW(i) < p.M) q[i] = *reinterpret_cast<const uint2*>(p.aux + OFF(i));
+      }
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M) {
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].y));
+          *reinterpret_cast<uint2*>(out + OFF(i)) =
+              make_uint2(pack_bf16(v[i].x * gelu_erf_grad(lo.x), v[i].y * gelu_erf_grad(lo.y)),
+                         pack_bf16(v[i].z * gelu_erf_grad(hi.x), v[i].w * gelu_erf_grad(hi.y)));
+        }
     } break;
-    case FC_EPI_F32:
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = a;
-      break;
-    case FC_EPI_ATOMIC_F32:
-      red_add_v4(reinterpret_cast<float*>(p.out) + o, p.alpha * a.x, p.alpha * a.y, p.alpha * a.z, p.alpha * a.w);
-      break;
+    case FC_EPI_F32: {
+      float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M) *reinterpret_cast<float4*>(out + OFF(i)) = v[i];
+    } break;
+    case FC_EPI_ATOMIC_F32: {
+      float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M)
+          red_add_v4(out + OFF(i), p.alpha * v[i].x, p.alpha * v[i].y, p.alpha * v[i].z, p.alpha * v[i].w);
+    } break;
     case FC_EPI_PATCH: {
       // row = b*P + t  ->  token row b*(P+1) + 1 + t of x; add pos_embed[1+t]
-      const int b = row / p.patches, t = row - b * p.patches;
-      const float4 e = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                 (static_cast<size_t>(b) * (p.patches + 1) + 1 + t) * p.ldo + col) =
-          make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
+      float4 e[8];
+      int orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        orow[i] = 0;
+        if (ROW(i) < p.M) {
+          const int b = ROW(i) / p.patches, t = ROW(i) - b * p.patches;
+          orow[i] = b * (p.patches + 1) + 1 + t;
+          e[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
+        }
+      }
+      float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ROW(i) < p.M)
+          *reinterpret_cast<float4*>(out + static_cast<size_t>(orow[i]) * p.ldo + col) =
+              make_float4(v[i].x + e[i].x, v[i].y + e[i].y, v[i].z + e[i].z, v[i].w + e[i].w);
     } break;
     default: break;
   }
+#undef ROW
+#undef OFF
 }
 
 // Persistent, warp-specialised: each CTA (one per SM) walks tiles  t = blockIdx.x, +gridDim.x, ...
@@ -158,7 +242,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full_bar[b], 1);
-        mbar_init(&tmem_empty_bar[b], 4);            // one arrival per epilogue warp
+        mbar_init(&tmem_empty_bar[b], EPI_WARPS);    // one arrival per epilogue warp
       }
       fence_barrier_init();
     }
@@ -236,8 +320,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    float* stage = epi_stage + q * (32 * STAGE_LD);
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int half = (warp - 2) >> 2;          // which of the two warps of that quarter: odd / even 32-col chunks
+    float* stage = epi_stage + (warp - 2) * (32 * STAGE_LD);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % tiles_mn;
@@ -246,14 +330,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      // chunks this warp owns: c = half, half+2, ... ; the last one it will actually read (col0 < N)
+      int last_c = -1;
+      for (int c = half; c < BN / 32; c += 2)
+        if (n0 + c * 32 < p.N) last_c = c;
+      if (last_c < 0) {                        // nothing to read in this tile: release immediately
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;                // warp-uniform
+      for (int c = half; c <= last_c; c += 2) {
         float acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
-        if (c == BN / 32 - 1 || col0 + 32 >= p.N) {   // last TMEM read of this tile: hand the buffer back
+        if (c == last_c) {                     // last TMEM read of this tile by this warp: hand the buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
@@ -264,12 +354,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j * 4) =
               make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 4 * i;
-          const float4 v = *reinterpret_cast<const float4*>(stage + r * STAGE_LD + c4);
-          epilogue_vec4(p, m0 + q * 32 + r, col0 + c4, v);
-        }
+        epilogue_block(p, stage, m0 + q * 32, n0 + c * 32, lane);
         __syncwarp();
       }
     }
