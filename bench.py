@@ -131,6 +131,7 @@ def run_ours(a):
     def timed_rounds(server, steps, warmup, sampler=None):
         per, agg_ms, agg_bytes = [], [], []
         samples = 0
+        phases = {"local_training": 0.0, "aggregation_and_refresh": 0.0}
         for it in range(warmup + steps):
             server.round += 1
             if world > 1:
@@ -155,6 +156,9 @@ def run_ours(a):
                 agg_ms.append(la["events"][0].elapsed_time(la["events"][1]))
                 agg_bytes.append(la["bytes"])
                 samples += sum(server.args.E * len(server.clients[i]) for i in ids)
+                for k in phases:
+                    phases[k] += server.phase_ms[k] / steps
+        timed_rounds.phases = phases
         t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -181,6 +185,7 @@ def run_ours(a):
     clocks = sampler.finish() if sampler is not None else None
     launches_timed = int(launches * a.steps / (a.steps + a.warmup))
     value = samples / (total_ms / 1e3)
+    phases = dict(timed_rounds.phases)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): one extra round with per-launch CUDA events ----
     L.fc_gemm_profile(1)
@@ -227,6 +232,8 @@ def run_ours(a):
                          "peak_source": pk["src"] + " sustained bf16", "traffic": None,
                          "launches_per_round": int(n_gemm), "avg_launch_us": round(ms.value * 1e3 / max(n_gemm, 1), 2),
                          "round_model_tflops": round(round_flops * n_gpus / (total_ms / a.steps * 1e-3) / 1e12 / n_gpus, 2)},
+            "phase_ms_host_clock": {k: round(v, 2) for k, v in phases.items()},
+            "train_phase_samples_per_s": round(samples / a.steps / (phases["local_training"] * 1e-3), 2),
             "aggregation": {"gbs": round(agg_best, 1), "frac_of_measured_hbm": round(agg_best / pk["hbm"], 4),
                             "bytes_per_round": int(agg_bytes[0]) if agg_bytes else 0,
                             "ms": round(sorted(agg_ms)[len(agg_ms) // 2], 4) if agg_ms else None},

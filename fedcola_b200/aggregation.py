@@ -270,10 +270,7 @@ class AggregationPlan:
         for k in order:
             a = self.host[k]
             buf[offs[k]:offs[k] + a.nbytes] = a.view(np.uint8).reshape(-1)
-        t = torch.from_numpy(buf)
-        if torch.cuda.is_available():
-            t = t.pin_memory()
-        self._dev_buf = t.to(device, non_blocking=True)
+        self._dev_buf = torch.from_numpy(buf).to(device)      # ~100 KB: a pageable copy beats a cudaHostAlloc
         base = self._dev_buf.data_ptr()
         self.dev = {k: base + offs[k] for k in order}
         self.device = torch.device(device)

@@ -16,7 +16,11 @@
 namespace {
 
 constexpr int HD = 64;        // head dim
-constexpr int LDS = 72;       // padded smem row (bf16 elements): 144 B -> conflict-free ldmatrix
+constexpr int LDS = 64;       // smem row = 128 B = 8 chunks of 16 B, XOR-swizzled by (row & 7): conflict-free ldmatrix
+                              // without padding, so the backward kernel's 4 staged matrices fit twice per SM
+
+// element offset of 16-byte chunk `chunk` (0..7) of row r
+__device__ __forceinline__ int swz(int r, int chunk) { return r * LDS + ((chunk ^ (r & 7)) << 3); }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -43,7 +47,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // A-operand fragments of a 16-row tile (rows r0..r0+15) for all 4 k16 steps of the 64-wide head dim.
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* s, int r0, int lane) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) ldsm_x4(a[kk], s + (r0 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8);
+  for (int kk = 0; kk < 4; ++kk) ldsm_x4(a[kk], s + swz(r0 + (lane & 15), kk * 2 + (lane >> 4)));
 }
 // acc(16 x 16 cols [c0, c0+16)) = A(16 x 64) * M[c0..c0+16, 0..64)^T — M rows are the "n" index, head dim is k.
 __device__ __forceinline__ void mma_rowsT(float (&acc)[2][4], const uint32_t (&a)[4][4], const __nv_bfloat16* m, int c0,
@@ -57,7 +61,7 @@ __device__ __forceinline__ void mma_rowsT(float (&acc)[2][4], const uint32_t (&a
 #pragma unroll
     for (int kk = 0; kk < 4; kk += 2) {
       uint32_t b[4];   // (n-tile j) x (k steps kk, kk+1)
-      ldsm_x4(b, m + (c0 + j * 8 + (lane & 7)) * LDS + kk * 16 + (lane >> 3) * 8);
+      ldsm_x4(b, m + swz(c0 + j * 8 + (lane & 7), kk * 2 + (lane >> 3)));
       mma16816(acc[j], a[kk], b[0], b[1]);
       mma16816(acc[j], a[kk + 1], b[2], b[3]);
     }
@@ -69,7 +73,7 @@ __device__ __forceinline__ void mma_rows(float (&out)[8][4], const uint32_t (&p)
 #pragma unroll
   for (int n = 0; n < 8; n += 2) {
     uint32_t b[4];
-    ldsm_x4_t(b, m + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n * 8 + (lane >> 4) * 8);
+    ldsm_x4_t(b, m + swz(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, n + (lane >> 4)));
     mma16816(out[n], p, b[0], b[1]);
     mma16816(out[n + 1], p, b[2], b[3]);
   }
@@ -82,7 +86,7 @@ __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < n) v = *reinterpret_cast<const uint4*>(src + (size_t)r * row_stride + c * 8);
-    *reinterpret_cast<uint4*>(dst + r * LDS + c * 8) = v;
+    *reinterpret_cast<uint4*>(dst + swz(r, c)) = v;
   }
 }
 
@@ -173,8 +177,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __re
 
 // ---- backward -----------------------------------------------------------------------------------
 // dV = P^T dO;  dP = dO V^T;  dS = P ⊙ (dP - D), D_i = sum_c dO_ic O_ic;  dQ = scale dS K;  dK = scale dS^T Q
-template <int NPAD>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+template <int NPAD, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                        const __nv_bfloat16* __restrict__ o_fwd,
                                                        const __nv_bfloat16* __restrict__ d_out,
                                                        const float* __restrict__ lse_g,
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __re
     float acc = 0.f;
     if (r < N) {
       const uint4 ov = *reinterpret_cast<const uint4*>(ofb + (size_t)r * d + c * 8);
-      const uint4 gv = *reinterpret_cast<const uint4*>(Gs + r * LDS + c * 8);
+      const uint4 gv = *reinterpret_cast<const uint4*>(Gs + swz(r, c));
       const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
       const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
 #pragma unroll
@@ -327,8 +331,10 @@ template <int NPAD>
 int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse,
                __nv_bfloat16* dqkv, int B, int N, int H, float scale, cudaStream_t st) {
   const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4;
-  FC_SMEM_OPT_IN(attn_bwd_kernel<NPAD>, smem);
-  attn_bwd_kernel<NPAD><<<B * H, 256, smem, st>>>(qkv, o, dout, lse, dqkv, N, H, scale);
+  // warps per CTA chosen so the NPAD/16 row tiles split evenly (13 tiles -> 7 warps x 2 rounds)
+  constexpr int NW = NPAD == 208 ? 7 : (NPAD == 256 ? 8 : 4);
+  FC_SMEM_OPT_IN((attn_bwd_kernel<NPAD, NW>), smem);
+  attn_bwd_kernel<NPAD, NW><<<B * H, NW * 32, smem, st>>>(qkv, o, dout, lse, dqkv, N, H, scale);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }

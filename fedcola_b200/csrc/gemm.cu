@@ -9,7 +9,7 @@
 // Persistent, warp-specialised kernel: one CTA per SM walks 128 x BN output tiles (BN = 128 / 192 / 256,
 // UMMA M=128, N=BN, K=16 per instruction).  A 4-6 stage TMA->smem ring of 64-wide K blocks (128-byte
 // swizzle) runs across tile boundaries; the fp32 accumulator is double-buffered in TMEM (2 x 256 columns)
-// so the 8 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
+// so the 12 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
 // K = 384..1536: short main loops, store-heavy epilogues.  The epilogue transposes each 32x32 accumulator
 // block through shared memory so that every global load/store of a warp covers whole 64/128-byte row
 // segments (resid / pre-activation reads and all writes are coalesced).
@@ -29,7 +29,7 @@ using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int EPI_WARPS = 12;              // three warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 constexpr int STAGE_LD = 36;               // floats per row of the epilogue transpose buffer (144 B: conflict-free)
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
@@ -66,8 +66,9 @@ struct GemmParams {
 //   Phi(x) = 0.5*(1 + erf(x/sqrt2));  with z = |x|/sqrt2, t = 1/(1 + p z):  1 - erf(z) = poly(t) * exp(-z^2)
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);                                             // = exp(-x^2/2), shared with the pdf term
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU.RCP (2 ulp)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));      // exp(-z^2) = exp(-x^2/2)
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
@@ -320,7 +321,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;          // which of the two warps of that quarter: odd / even 32-col chunks
+    constexpr int WPQ = EPI_WARPS / 4;         // warps per lane quarter
+    const int half = (warp - 2) >> 2;          // which warp of that quarter: chunks c = half, half + WPQ, ...
     float* stage = epi_stage + (warp - 2) * (32 * STAGE_LD);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -332,14 +334,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
       // chunks this warp owns: c = half, half+2, ... ; the last one it will actually read (col0 < N)
       int last_c = -1;
-      for (int c = half; c < BN / 32; c += 2)
+      for (int c = half; c < BN / 32; c += WPQ)
         if (n0 + c * 32 < p.N) last_c = c;
       if (last_c < 0) {                        // nothing to read in this tile: release immediately
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       }
 #pragma unroll 1
-      for (int c = half; c <= last_c; c += 2) {
+      for (int c = half; c <= last_c; c += WPQ) {
         float acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
