@@ -121,7 +121,7 @@ def run_ours(a):
     pk = peaks()
 
     def make_server(resident):
-        args = workload_args(n_gpus, data_resident=resident, server_device=str(dev))
+        args = workload_args(n_gpus, data_resident=resident, server_device=str(dev), num_thread=a.threads)
         random.seed(args.seed)
         torch.manual_seed(args.seed)
         cds = make_client_datasets(client_specs(n_gpus), seq_len=SEQ, share=True)
@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--threads", type=int, default=1, help="client worker threads per GPU (args.num_thread)")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     a = ap.parse_args()
     if a.impl == "reference":

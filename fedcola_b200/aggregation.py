@@ -286,3 +286,34 @@ class AggregationPlan:
                             vp(d["coef"]), int(grid_ctas), self.device.index or 0,
                             _lib.stream_ptr(self.device))
         _lib.check(rc, "fc_aggregate")
+
+
+def shard_owner(position, world_size):
+    """Rank that trains the client at `position` of the sorted sampled-id list — the reference's
+    `cuda:(i % ngpu)` placement rule (fedavgserver.py:310-311), one process per GPU."""
+    return position % world_size
+
+
+def sharded_aggregate(globals_, clients, param_scope, flags, dist, rank, execute=None):
+    """Multi-GPU aggregation: every rank folds ITS clients (those with an arena) into closed-form
+    partial sums, one all-reduce (NCCL over NVLink on the GPU box; gloo in the CPU tests) finishes them, and
+    every rank ends with the same new global arenas.  `execute(plan)` runs the plan tables (default: the
+    CUDA kernel).  Returns the plan (for byte accounting)."""
+    parts = []
+    for g in globals_:
+        # regions the plan does not write (aux_weight, cross_modal_scale, padding) must survive the sum:
+        # rank 0 contributes the old arena, the others zeros
+        part = g.arena_in.clone() if rank == 0 else torch.zeros_like(g.arena_in)
+        g.arena_out = part
+        parts.append(part)
+    plan = AggregationPlan(globals_, clients, param_scope, mode=WSUM, include_global_term=(rank == 0), **flags)
+    if execute is None:
+        plan.to_device(globals_[0].arena_in.device).launch()
+    else:
+        execute(plan)
+    works = [dist.all_reduce(p, op=dist.ReduceOp.SUM, async_op=True) for p in parts]
+    for w in works:
+        w.wait()
+    for g, p in zip(globals_, parts):
+        g.arena_in.copy_(p)
+    return plan

@@ -90,6 +90,23 @@ __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat
   }
 }
 
+// Column sums over the 16 rows of a warp tile of two packed bf16 pairs (rows g and g+8, columns 2t, 2t+1):
+// reduce over the 8 row groups with shuffles, then lanes 0..3 add into shared memory.
+__device__ __forceinline__ void tile_colsum(float* dst, uint32_t w0, uint32_t w1, int lane) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+  float x = a.x + b.x, y = a.y + b.y;
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+  }
+  if (lane < 4) {
+    atomicAdd(dst, x);
+    atomicAdd(dst + 1, y);
+  }
+}
+
 // ---- forward ------------------------------------------------------------------------------------
 template <int NPAD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
@@ -182,7 +199,8 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
                                                        const __nv_bfloat16* __restrict__ o_fwd,
                                                        const __nv_bfloat16* __restrict__ d_out,
                                                        const float* __restrict__ lse_g,
-                                                       __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+                                                       __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
+                                                       int N, int H, float scale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* Ks = Qs + NPAD * LDS;
@@ -190,6 +208,7 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
   __nv_bfloat16* Gs = Vs + NPAD * LDS;                       // dO
   float* lse = reinterpret_cast<float*>(Gs + NPAD * LDS);    // [NPAD]
   float* Dr = lse + NPAD;                                    // [NPAD]
+  float* s_db = Dr + NPAD;                                   // [3*64] column sums of dQ | dK | dV of this head
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int d = H * HD;
   const long long rs = 3LL * d;
@@ -201,6 +220,7 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
   stage_rows(Vs, base + 2 * d, rs, N, NPAD);
   stage_rows(Gs, gb, d, N, NPAD);
   for (int r = threadIdx.x; r < NPAD; r += blockDim.x) lse[r] = r < N ? lse_g[((size_t)b * H + h) * N + r] : INFINITY;
+  for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x) s_db[i] = 0.f;
   __syncthreads();
   // D_i = <dO_i, O_i>: 8 lanes per row, 8 elements each
   for (int i = threadIdx.x; i < NPAD * 8; i += blockDim.x) {
@@ -262,10 +282,10 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
     }
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      if (row0 < N)
-        *reinterpret_cast<uint32_t*>(dq_base + (size_t)row0 * rs + n * 8 + 2 * t) = pack2(dq[n][0] * scale, dq[n][1] * scale);
-      if (row1 < N)
-        *reinterpret_cast<uint32_t*>(dq_base + (size_t)row1 * rs + n * 8 + 2 * t) = pack2(dq[n][2] * scale, dq[n][3] * scale);
+      const uint32_t w0 = pack2(dq[n][0] * scale, dq[n][1] * scale), w1 = pack2(dq[n][2] * scale, dq[n][3] * scale);
+      if (row0 < N) *reinterpret_cast<uint32_t*>(dq_base + (size_t)row0 * rs + n * 8 + 2 * t) = w0;
+      if (row1 < N) *reinterpret_cast<uint32_t*>(dq_base + (size_t)row1 * rs + n * 8 + 2 * t) = w1;
+      if (dbias != nullptr) tile_colsum(s_db + n * 8 + 2 * t, row0 < N ? w0 : 0u, row1 < N ? w1 : 0u, lane);
     }
   }
 
@@ -306,15 +326,26 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
     }
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
+      const uint32_t k0 = pack2(dk[n][0] * scale, dk[n][1] * scale), k1 = pack2(dk[n][2] * scale, dk[n][3] * scale);
+      const uint32_t v0 = pack2(dv[n][0], dv[n][1]), v1 = pack2(dv[n][2], dv[n][3]);
       if (key0 < N) {
-        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key0 * rs + n * 8 + 2 * t) = pack2(dk[n][0] * scale, dk[n][1] * scale);
-        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key0 * rs + n * 8 + 2 * t) = pack2(dv[n][0], dv[n][1]);
+        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key0 * rs + n * 8 + 2 * t) = k0;
+        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key0 * rs + n * 8 + 2 * t) = v0;
       }
       if (key1 < N) {
-        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key1 * rs + n * 8 + 2 * t) = pack2(dk[n][2] * scale, dk[n][3] * scale);
-        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key1 * rs + n * 8 + 2 * t) = pack2(dv[n][2], dv[n][3]);
+        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key1 * rs + n * 8 + 2 * t) = k1;
+        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key1 * rs + n * 8 + 2 * t) = v1;
+      }
+      if (dbias != nullptr) {
+        tile_colsum(s_db + HD + n * 8 + 2 * t, key0 < N ? k0 : 0u, key1 < N ? k1 : 0u, lane);
+        tile_colsum(s_db + 2 * HD + n * 8 + 2 * t, key0 < N ? v0 : 0u, key1 < N ? v1 : 0u, lane);
       }
     }
+  }
+  if (dbias != nullptr) {     // one global atomic per column per head: qkv bias gradient [3][H][64]
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x)
+      atomicAdd(dbias + (i / HD) * d + h * HD + (i % HD), s_db[i]);
   }
 }
 
@@ -329,12 +360,12 @@ int launch_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, 
 }
 template <int NPAD>
 int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse,
-               __nv_bfloat16* dqkv, int B, int N, int H, float scale, cudaStream_t st) {
-  const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4;
+               __nv_bfloat16* dqkv, float* dbias, int B, int N, int H, float scale, cudaStream_t st) {
+  const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4 + 3 * HD * 4;
   // warps per CTA chosen so the NPAD/16 row tiles split evenly (13 tiles -> 7 warps x 2 rounds)
   constexpr int NW = NPAD == 208 ? 7 : (NPAD == 256 ? 8 : 4);
   FC_SMEM_OPT_IN((attn_bwd_kernel<NPAD, NW>), smem);
-  attn_bwd_kernel<NPAD, NW><<<B * H, NW * 32, smem, st>>>(qkv, o, dout, lse, dqkv, N, H, scale);
+  attn_bwd_kernel<NPAD, NW><<<B * H, NW * 32, smem, st>>>(qkv, o, dout, lse, dqkv, dbias, N, H, scale);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
@@ -357,7 +388,7 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
 }
 
 extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
-                                int B, int N, int H, int head_dim, int device, void* stream) {
+                                float* dbias, int B, int N, int H, int head_dim, int device, void* stream) {
   FC_REQUIRE(head_dim == HD, "fc_attention_bwd: head_dim must be 64 (got %d)", head_dim);
   FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0, "fc_attention_bwd: unsupported shape B=%d N=%d H=%d", B, N, H);
   FcDeviceGuard guard(device);
@@ -367,8 +398,8 @@ extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_
   auto g = reinterpret_cast<const __nv_bfloat16*>(d_out);
   auto dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N <= 48) return launch_bwd<48>(q, o, g, lse, dq, B, N, H, scale, st);
-  if (N <= 64) return launch_bwd<64>(q, o, g, lse, dq, B, N, H, scale, st);
-  if (N <= 208) return launch_bwd<208>(q, o, g, lse, dq, B, N, H, scale, st);
-  return launch_bwd<256>(q, o, g, lse, dq, B, N, H, scale, st);
+  if (N <= 48) return launch_bwd<48>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
+  if (N <= 64) return launch_bwd<64>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
+  if (N <= 208) return launch_bwd<208>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
+  return launch_bwd<256>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
 }

@@ -3,7 +3,7 @@
 // Replaces the cuBLAS sgemm calls behind every nn.Linear / CrossModalReparamLinear of the reference's
 // Block (/root/reference/src/models/mome.py:58-60,112-121,143-166) and the PatchEmbed conv (:252-265),
 // forward and backward, with the elementwise work that follows each of them fused into the epilogue:
-//   bias, exact-erf GELU (fwd + derivative), DropPath-scaled residual add, patch-row remap + pos_embed,
+//   bias, exact-erf GELU (value + derivative in one pass), multiply-by-saved-derivative (+ bias-gradient column sums), DropPath-scaled residual add, patch-row remap + pos_embed,
 //   split-K gradient accumulation.
 //
 // Persistent, warp-specialised kernel: one CTA per SM walks 128 x BN output tiles (BN = 128 / 192 / 256,
@@ -54,7 +54,8 @@ struct GemmParams {
   const float* resid;       // EPI_RESID: fp32 [M, ldo]
   const float* row_scale;   // per-group scale (DropPath keep/keep_prob), index = row / rows_per_group; or null
   int rows_per_group;
-  const __nv_bfloat16* aux; // EPI_DGELU: pre-activation bf16 [M, ldo]
+  const __nv_bfloat16* aux; // EPI_MULAUX: bf16 multiplier [M, ldo] (gelu'(pre) saved by the forward)
+  float* colsum;            // EPI_MULAUX: += column sums of the output (bias gradient), or null
   const float* pos;         // EPI_PATCH: pos_embed [(P+1), N]
   int patches;              // EPI_PATCH: P (196)
   float alpha;
@@ -100,9 +101,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // of a block are issued before the first dependent use, so their latency is paid once per block.
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float* stage, int row_base, int col0, int lane) {
   const int rsub = lane >> 3, col = col0 + (lane & 7) * 4;
-  if (col >= p.N) return;                       // N is a multiple of 8, col a multiple of 4
+  if (col >= p.N && p.colsum == nullptr) return;   // N is a multiple of 8, col a multiple of 4
+  const bool col_ok = col < p.N;                 // (with colsum the whole warp stays for the shuffles)
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  if (p.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   float4 v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -110,7 +112,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
     v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w;
   }
   const int r0 = row_base + rsub;
-#define ROW(i) (r0 + 4 * (i))
+#define ROW(i) (col_ok ? r0 + 4 * (i) : p.M)
 #define OFF(i) (static_cast<size_t>(ROW(i)) * p.ldo + col)
   switch (p.epi) {
     case FC_EPI_BF16: {
@@ -121,14 +123,23 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
           *reinterpret_cast<uint2*>(out + OFF(i)) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
     } break;
     case FC_EPI_GELU: {
+      // out = gelu'(pre) (what the backward needs), out2 = gelu(pre) (the fc2 operand); Phi and exp are shared
       __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out);
       __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (ROW(i) < p.M) {
-          *reinterpret_cast<uint2*>(o1 + OFF(i)) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
-          *reinterpret_cast<uint2*>(o2 + OFF(i)) = make_uint2(pack_bf16(gelu_erf(v[i].x), gelu_erf(v[i].y)),
-                                                              pack_bf16(gelu_erf(v[i].z), gelu_erf(v[i].w)));
+          float g[4], d[4];
+          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float cdf, e;
+            gelu_parts(x[k], cdf, e);
+            g[k] = x[k] * cdf;
+            d[k] = fmaf(x[k] * 0.39894228040143267794f, e, cdf);
+          }
+          *reinterpret_cast<uint2*>(o1 + OFF(i)) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
+          *reinterpret_cast<uint2*>(o2 + OFF(i)) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
         }
     } break;
     case FC_EPI_RESID: {
@@ -150,7 +161,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
           *reinterpret_cast<float4*>(out + OFF(i)) = make_float4(x[i].x + sc[i] * v[i].x, x[i].y + sc[i] * v[i].y,
                                                                  x[i].z + sc[i] * v[i].z, x[i].w + sc[i] * v[i].w);
     } break;
-    case FC_EPI_DGELU: {
+    case FC_EPI_MULAUX: {
       uint2 q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -158,15 +169,28 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
         if (ROW(i) < p.M) q[i] = *reinterpret_cast<const uint2*>(p.aux + OFF(i));
       }
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (ROW(i) < p.M) {
           const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].x));
           const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].y));
-          *reinterpret_cast<uint2*>(out + OFF(i)) =
-              make_uint2(pack_bf16(v[i].x * gelu_erf_grad(lo.x), v[i].y * gelu_erf_grad(lo.y)),
-                         pack_bf16(v[i].z * gelu_erf_grad(hi.x), v[i].w * gelu_erf_grad(hi.y)));
+          const uint32_t w0 = pack_bf16(v[i].x * lo.x, v[i].y * lo.y), w1 = pack_bf16(v[i].z * hi.x, v[i].w * hi.y);
+          *reinterpret_cast<uint2*>(out + OFF(i)) = make_uint2(w0, w1);
+          if (p.colsum != nullptr) {      // sum what was actually stored (bf16-rounded), as a separate pass would
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+            cs.x += a.x; cs.y += a.y; cs.z += b.x; cs.w += b.y;
+          }
         }
+      if (p.colsum != nullptr) {          // 32 rows of this block: lanes l, l+8, l+16, l+24 share the columns
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
+        if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs.x, cs.y, cs.z, cs.w);
+      }
     } break;
     case FC_EPI_F32: {
       float* out = reinterpret_cast<float*>(p.out);
@@ -484,15 +508,16 @@ extern "C" long long fc_gemm_profile_collect(double* total_ms, double* total_flo
 extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
                             long long ldb, int b_mn_major, int epi, void* out, void* out2, long long ldo,
                             const float* bias, const float* resid, const float* row_scale, int rows_per_group,
-                            const void* aux, const float* pos, int patches, float alpha, int splits, int device,
-                            void* stream) {
+                            const void* aux, const float* pos, int patches, float alpha, int splits,
+                            float* colsum, int device, void* stream) {
   FC_REQUIRE(M > 0 && N > 0 && K > 0, "fc_gemm_bf16: empty problem %d %d %d", M, N, K);
   FC_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 4 == 0, "fc_gemm_bf16: N, lda, ldb must be multiples of 8");
   FC_REQUIRE(epi >= FC_EPI_BF16 && epi <= FC_EPI_PATCH, "fc_gemm_bf16: bad epilogue %d", epi);
   FC_REQUIRE(out != nullptr, "fc_gemm_bf16: null output");
   FC_REQUIRE(epi != FC_EPI_GELU || out2 != nullptr, "fc_gemm_bf16: GELU epilogue needs out2");
   FC_REQUIRE(epi != FC_EPI_RESID || resid != nullptr, "fc_gemm_bf16: RESID epilogue needs resid");
-  FC_REQUIRE(epi != FC_EPI_DGELU || aux != nullptr, "fc_gemm_bf16: DGELU epilogue needs aux");
+  FC_REQUIRE(epi != FC_EPI_MULAUX || aux != nullptr, "fc_gemm_bf16: MULAUX epilogue needs aux");
+  FC_REQUIRE(colsum == nullptr || epi == FC_EPI_MULAUX, "fc_gemm_bf16: colsum is only fused into the MULAUX epilogue");
   FC_REQUIRE(epi != FC_EPI_PATCH || (pos != nullptr && patches > 0), "fc_gemm_bf16: PATCH epilogue needs pos");
   FC_REQUIRE(row_scale == nullptr || rows_per_group > 0, "fc_gemm_bf16: rows_per_group");
   FcDeviceGuard guard(device);
@@ -529,6 +554,7 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   p.out = out; p.out2 = out2; p.bias = bias; p.resid = resid; p.row_scale = row_scale;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux); p.pos = pos; p.patches = patches; p.alpha = alpha;
+  p.colsum = colsum;
   CUtensorMap ta, tb;
   int rc;
   // K-major operand: global [rows, K]; MN-major operand: global [K, rows].

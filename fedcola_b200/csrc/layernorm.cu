@@ -83,14 +83,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      __nv_bfloat16* __restrict__ dxs, long long dxs_row_stride,
                                                      const float* __restrict__ row_scale,
                                                      int rows_per_group, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows, int d) {
-  extern __shared__ float s_part[];   // [2][warps_per_block][d]
+                                                     float* __restrict__ dbeta, float* __restrict__ dxs_colsum,
+                                                     int rows, int d) {
+  extern __shared__ float s_part[];   // [3][warps_per_block][d]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int warp = blockIdx.x * wpb + wib, nwarps = gridDim.x * wpb;
   const int nvec = d >> 2;
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], dc[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int row = warp; row < rows; row += nwarps) {
     const float m = mean[row], r = rstd[row];
@@ -138,33 +139,45 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
         }
         *dxr = o;
-        if (dxs)
-          reinterpret_cast<uint2*>(dxs + (size_t)row * dxs_row_stride)[c] =
-              make_uint2(pack2(o.x * sc, o.y * sc), pack2(o.z * sc, o.w * sc));
+        if (dxs) {
+          const uint32_t w0 = pack2(o.x * sc, o.y * sc), w1 = pack2(o.z * sc, o.w * sc);
+          reinterpret_cast<uint2*>(dxs + (size_t)row * dxs_row_stride)[c] = make_uint2(w0, w1);
+          if (dxs_colsum) {     // bias gradient of the Linear that consumes dxs: sum the bf16 values it will read
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+            dc[i].x += a.x; dc[i].y += a.y; dc[i].z += b.x; dc[i].w += b.y;
+          }
+        }
       }
     }
   }
-  if (dgamma == nullptr) return;
+  if (dgamma == nullptr && dxs_colsum == nullptr) return;
   // block-level reduction of the per-warp column partials, then one atomicAdd per column per block
   float* pg = s_part;
   float* pb = s_part + wpb * d;
+  float* pc = s_part + 2 * wpb * d;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
       reinterpret_cast<float4*>(pg + wib * d)[c] = dg[i];
       reinterpret_cast<float4*>(pb + wib * d)[c] = db[i];
+      reinterpret_cast<float4*>(pc + wib * d)[c] = dc[i];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, e = 0.f;
     for (int w = 0; w < wpb; ++w) {
       a += pg[w * d + c];
       b += pb[w * d + c];
+      e += pc[w * d + c];
     }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+    if (dgamma != nullptr) {
+      atomicAdd(dgamma + c, a);
+      atomicAdd(dbeta + c, b);
+    }
+    if (dxs_colsum != nullptr) atomicAdd(dxs_colsum + c, e);
   }
 }
 
@@ -196,17 +209,18 @@ extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row
                                 long long x_row_stride, const float* mean, const float* rstd, const float* gamma,
                                 float* dx, long long dx_row_stride, int accumulate, void* dxs_bf16,
                                 long long dxs_row_stride, const float* row_scale, int rows_per_group, float* dgamma,
-                                float* dbeta, int rows, int d, int device, void* stream) {
+                                float* dbeta, float* dxs_colsum, int rows, int d, int device, void* stream) {
   FC_REQUIRE(rows >= 0 && d > 0 && d % 4 == 0 && d <= kMaxVec * 128, "fc_layernorm_bwd: d=%d unsupported", d);
   FC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "fc_layernorm_bwd: dgamma/dbeta must both be given");
   FC_REQUIRE(row_scale == nullptr || rows_per_group > 0, "fc_layernorm_bwd: rows_per_group");
+  FC_REQUIRE(dxs_colsum == nullptr || dxs_bf16 != nullptr, "fc_layernorm_bwd: dxs_colsum needs dxs");
   if (rows == 0) return FC_OK;
   FcDeviceGuard guard(device);
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
   const int cap = fc_num_sms(device) * 4;     // 4 CTAs/SM; one atomicAdd per column per CTA for dgamma/dbeta
   if (grid > cap) grid = cap;
-  const size_t smem = dgamma ? sizeof(float) * 2 * wpb * d : 0;
+  const size_t smem = (dgamma || dxs_colsum) ? sizeof(float) * 3 * wpb * d : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   auto dxs = reinterpret_cast<__nv_bfloat16*>(dxs_bf16);
   const int rpg = rows_per_group > 0 ? rows_per_group : 1;
@@ -216,12 +230,12 @@ extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row
       if (smem > 48 * 1024) FC_SMEM_OPT_IN((ln_bwd_kernel<NV, true>), smem);                                       \
       ln_bwd_kernel<NV, true><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx, \
                                                            dx_row_stride, accumulate, dxs, dxs_row_stride, row_scale, \
-                                                           rpg, dgamma, dbeta, rows, d);                           \
+                                                           rpg, dgamma, dbeta, dxs_colsum, rows, d);               \
     } else {                                                                                                       \
       if (smem > 48 * 1024) FC_SMEM_OPT_IN((ln_bwd_kernel<NV, false>), smem);                                      \
       ln_bwd_kernel<NV, false><<<grid, wpb * 32, smem, st>>>(dy, dy_row_stride, x, x_row_stride, mean, rstd, gamma, dx, \
                                                             dx_row_stride, accumulate, dxs, dxs_row_stride, row_scale, \
-                                                            rpg, dgamma, dbeta, rows, d);                          \
+                                                            rpg, dgamma, dbeta, dxs_colsum, rows, d);              \
     }                                                                                                              \
   } while (0)
   const int nv = (d + 127) / 128;

@@ -23,7 +23,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 struct EncWs {
   float* x_in[FC_MAX_DEPTH + 1];
   float* x_mid[FC_MAX_DEPTH];
-  __nv_bfloat16 *ln1[FC_MAX_DEPTH], *ln2[FC_MAX_DEPTH], *qkv[FC_MAX_DEPTH], *ao[FC_MAX_DEPTH], *hpre[FC_MAX_DEPTH],
+  __nv_bfloat16 *ln1[FC_MAX_DEPTH], *ln2[FC_MAX_DEPTH], *qkv[FC_MAX_DEPTH], *ao[FC_MAX_DEPTH], *hgrad[FC_MAX_DEPTH],
       *hact[FC_MAX_DEPTH];
   float *mean1[FC_MAX_DEPTH], *rstd1[FC_MAX_DEPTH], *mean2[FC_MAX_DEPTH], *rstd2[FC_MAX_DEPTH], *lse[FC_MAX_DEPTH];
   __nv_bfloat16* patches;     // img: [B*P, 768]
@@ -70,7 +70,7 @@ void carve(const fc_mat_desc* m, int B, void* base, Ws* w) {
       s.ln2[j] = c.take<__nv_bfloat16>(T * d);
       s.qkv[j] = c.take<__nv_bfloat16>(T * 3 * d);
       s.ao[j] = c.take<__nv_bfloat16>(T * d);
-      s.hpre[j] = c.take<__nv_bfloat16>(T * hid);
+      s.hgrad[j] = c.take<__nv_bfloat16>(T * hid);
       s.hact[j] = c.take<__nv_bfloat16>(T * hid);
       s.mean1[j] = c.take<float>(T);
       s.rstd1[j] = c.take<float>(T);
@@ -132,9 +132,10 @@ struct Ctx {
 
 int gemm(const Ctx& c, int M, int N, int K, const void* A, long long lda, int a_mn, const void* Bm, long long ldb,
          int b_mn, int epi, void* out, void* out2, long long ldo, const float* bias, const float* resid,
-         const float* row_scale, int rpg, const void* aux, const float* pos, int patches, int splits) {
+         const float* row_scale, int rpg, const void* aux, const float* pos, int patches, int splits,
+         float* colsum = nullptr) {
   return fc_gemm_bf16(M, N, K, A, lda, a_mn, Bm, ldb, b_mn, epi, out, out2, ldo, bias, resid, row_scale, rpg, aux, pos,
-                      patches, 1.0f, splits, c.device, c.stream);
+                      patches, 1.0f, splits, colsum, c.device, c.stream);
 }
 
 // dW[rows_out, cols_out] += dY[T, rows_out]^T X[T, cols_out]   (both operands MN-major, split-K over tokens)
@@ -171,7 +172,7 @@ int encoder_forward(const Ctx& c, Ws& w, int e, const float* img, const long lon
              s.x_in[j], c.dp(e, j, 0), N, nullptr, nullptr, 0, 1));
     TRY(fc_layernorm_fwd(s.x_mid[j], d, c.p(o[N2W]), c.p(o[N2B]), 1e-5f, s.ln2[j], nullptr, s.mean2[j], s.rstd2[j], T,
                          d, c.device, c.stream));
-    TRY(gemm(c, T, hid, d, s.ln2[j], d, 0, c.ops + op[L_FC1], d, 0, FC_EPI_GELU, s.hpre[j], s.hact[j], hid,
+    TRY(gemm(c, T, hid, d, s.ln2[j], d, 0, c.ops + op[L_FC1], d, 0, FC_EPI_GELU, s.hgrad[j], s.hact[j], hid,
              c.p(o[FC1B]), nullptr, nullptr, 0, nullptr, nullptr, 0, 1));
     TRY(gemm(c, T, d, hid, s.hact[j], hid, 0, c.ops + op[L_FC2], hid, 0, FC_EPI_RESID, s.x_in[j + 1], nullptr, d,
              c.p(o[FC2B]), s.x_mid[j], c.dp(e, j, 1), N, nullptr, nullptr, 0, 1));
@@ -194,33 +195,32 @@ int encoder_backward(const Ctx& c, Ws& w, int e, const long long* ids) {
   // final norm backward on the cls rows; dxs = DropPath scale of the last block's mlp branch * dx
   TRY(fc_layernorm_bwd(s.dfeat, 0, d, s.x_in[L], (long long)N * d, s.mean_f, s.rstd_f, c.p(m->norm_w), s.dx,
                        (long long)N * d, 0, s.dxs, (long long)N * d, c.dp(e, L - 1, 1), 1, c.g(m->norm_w),
-                       c.g(m->norm_b), B, d, c.device, c.stream));
+                       c.g(m->norm_b), c.g(m->blk[e][L - 1][FC2B]), B, d, c.device, c.stream));
   for (int j = L - 1; j >= 0; --j) {
     const long long* o = m->blk[e][j];
     const long long* op = m->op[e][j];
     // ---- mlp branch:  x_out = x_mid + dp2 * (fc2(gelu(fc1(LN2(x_mid)))))
-    TRY(gemm(c, T, hid, d, s.dxs, d, 0, c.ops + op[L_FC2], hid, 1, FC_EPI_DGELU, s.d_h, nullptr, hid, nullptr, nullptr,
-             nullptr, 0, s.hpre[j], nullptr, 0, 1));
+    // (fc2 bias gradient = column sums of dxs: accumulated by the LayerNorm backward that produced dxs)
+    TRY(gemm(c, T, hid, d, s.dxs, d, 0, c.ops + op[L_FC2], hid, 1, FC_EPI_MULAUX, s.d_h, nullptr, hid, nullptr, nullptr,
+             nullptr, 0, s.hgrad[j], nullptr, 0, 1, c.g(o[FC1B])));     // d_h = (dxs W2) * gelu'(pre); fc1 bias grad fused
     TRY(gemm_dw(c, d, hid, T, s.dxs, s.hact[j], c.g(o[FC2W])));
-    TRY(fc_colsum_bf16(s.dxs, d, T, d, c.g(o[FC2B]), c.device, c.stream));
     TRY(gemm(c, T, d, hid, s.d_h, hid, 0, c.ops + op[L_FC1], d, 1, FC_EPI_BF16, s.d_ln, nullptr, d, nullptr, nullptr,
              nullptr, 0, nullptr, nullptr, 0, 1));
     TRY(gemm_dw(c, hid, d, T, s.d_h, s.ln2[j], c.g(o[FC1W])));
-    TRY(fc_colsum_bf16(s.d_h, hid, T, hid, c.g(o[FC1B]), c.device, c.stream));
     TRY(fc_layernorm_bwd(s.d_ln, 1, d, s.x_mid[j], d, s.mean2[j], s.rstd2[j], c.p(o[N2W]), s.dx, d, 1, s.dxs, d,
-                         c.dp(e, j, 0), N, c.g(o[N2W]), c.g(o[N2B]), T, d, c.device, c.stream));
+                         c.dp(e, j, 0), N, c.g(o[N2W]), c.g(o[N2B]), c.g(o[PROJB]), T, d, c.device, c.stream));
     // ---- attention branch:  x_mid = x_in + dp1 * proj(attn(qkv(LN1(x_in))))
     TRY(gemm(c, T, d, d, s.dxs, d, 0, c.ops + op[L_PROJ], d, 1, FC_EPI_BF16, s.d_ao, nullptr, d, nullptr, nullptr,
              nullptr, 0, nullptr, nullptr, 0, 1));
     TRY(gemm_dw(c, d, d, T, s.dxs, s.ao[j], c.g(o[PROJW])));
-    TRY(fc_colsum_bf16(s.dxs, d, T, d, c.g(o[PROJB]), c.device, c.stream));
-    TRY(fc_attention_bwd(s.qkv[j], s.ao[j], s.d_ao, s.lse[j], s.d_qkv, B, N, H, d / H, c.device, c.stream));
+    TRY(fc_attention_bwd(s.qkv[j], s.ao[j], s.d_ao, s.lse[j], s.d_qkv, c.g(o[QKVB]), B, N, H, d / H, c.device,
+                         c.stream));
     TRY(gemm(c, T, d, 3 * d, s.d_qkv, 3 * d, 0, c.ops + op[L_QKV], d, 1, FC_EPI_BF16, s.d_ln, nullptr, d, nullptr,
              nullptr, nullptr, 0, nullptr, nullptr, 0, 1));
     TRY(gemm_dw(c, 3 * d, d, T, s.d_qkv, s.ln1[j], c.g(o[QKVW])));
-    TRY(fc_colsum_bf16(s.d_qkv, 3 * d, T, 3 * d, c.g(o[QKVB]), c.device, c.stream));
     TRY(fc_layernorm_bwd(s.d_ln, 1, d, s.x_in[j], d, s.mean1[j], s.rstd1[j], c.p(o[N1W]), s.dx, d, 1, s.dxs, d,
-                         j > 0 ? c.dp(e, j - 1, 1) : nullptr, N, c.g(o[N1W]), c.g(o[N1B]), T, d, c.device, c.stream));
+                         j > 0 ? c.dp(e, j - 1, 1) : nullptr, N, c.g(o[N1W]), c.g(o[N1B]),
+                         j > 0 ? c.g(m->blk[e][j - 1][FC2B]) : nullptr, T, d, c.device, c.stream));
   }
   if (e == 0) {
     TRY(fc_patch_bwd_prep(s.dx, s.dxp, c.g(m->img_pos), c.g(m->img_cls), c.g(m->img_pb), B, m->patches, d, c.device,

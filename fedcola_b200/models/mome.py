@@ -96,10 +96,7 @@ class ModalityAgnosticTransformer(nn.Module):
         for seg in self.spec.segments:
             parts = seg.key.split(".")
             if seg.alias_of is not None:
-                # share_scope == 'all': blockses.<none_idx> *is* blockses.<main_idx> (mome.py:824-827)
-                src = seg.alias_of.split(".")
-                self._modules["blockses"]._modules[parts[1]] = self._modules["blockses"]._modules[src[1]]
-                continue
+                continue          # bound below, once the main encoder exists
             node = self
             for p in parts[:-1]:
                 if p not in node._modules or node._modules[p] is None:
@@ -109,6 +106,11 @@ class ModalityAgnosticTransformer(nn.Module):
             param = nn.Parameter(view, requires_grad=old_flags.get(seg.key, seg.requires_grad))
             node._parameters[parts[-1]] = param
             made[seg.key] = param
+        for seg in self.spec.segments:
+            if seg.alias_of is not None:
+                # share_scope == 'all': blockses.<none_idx> *is* blockses.<main_idx> (mome.py:824-827)
+                dst, src = seg.key.split(".")[1], seg.alias_of.split(".")[1]
+                self._modules["blockses"]._modules[dst] = self._modules["blockses"]._modules[src]
         # None placeholders, as in the reference's ModuleLists
         for grp in ("embeddings", "blockses", "heads"):
             if grp not in self._modules:

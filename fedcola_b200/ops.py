@@ -6,7 +6,7 @@ import torch
 from . import _lib
 from ._lib import c_f, c_int, c_ll, c_vp, ptr
 
-EPI_BF16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_F32, EPI_ATOMIC_F32, EPI_PATCH = range(7)
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_MULAUX, EPI_F32, EPI_ATOMIC_F32, EPI_PATCH = range(7)
 
 
 def _dev(t):
@@ -15,7 +15,7 @@ def _dev(t):
 
 
 def gemm_bf16(A, B, epi, out, *, a_mn=False, b_mn=False, out2=None, bias=None, resid=None, row_scale=None,
-              rows_per_group=0, aux=None, pos=None, patches=0, alpha=1.0, splits=1):
+              rows_per_group=0, aux=None, pos=None, patches=0, alpha=1.0, splits=1, colsum=None):
     """out[M,N] (+)= A · Bᵀ with the fused epilogue `epi` (see include/fedcola_b200.h).
     A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn); bf16, row-major, last dim contiguous."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -28,7 +28,7 @@ def gemm_bf16(A, B, epi, out, *, a_mn=False, b_mn=False, out2=None, bias=None, r
     rc = _lib.lib().fc_gemm_bf16(c_int(M), c_int(N), c_int(K), ptr(A), c_ll(A.stride(0)), c_int(int(a_mn)), ptr(B),
                                  c_ll(B.stride(0)), c_int(int(b_mn)), c_int(epi), ptr(out), ptr(out2), c_ll(ldo),
                                  ptr(bias), ptr(resid), ptr(row_scale), c_int(rows_per_group), ptr(aux), ptr(pos),
-                                 c_int(patches), c_f(alpha), c_int(splits), c_int(dev), _lib.stream_ptr(A.device))
+                                 c_int(patches), c_f(alpha), c_int(splits), ptr(colsum), c_int(dev), _lib.stream_ptr(A.device))
     _lib.check(rc, "fc_gemm_bf16")
     return out
 
@@ -47,9 +47,9 @@ def attention_fwd(qkv, B, N, H, want_lse=True):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B, N, H):
+def attention_bwd(qkv, out, dout, lse, B, N, H, dbias=None):
     dqkv = torch.empty_like(qkv)
-    rc = _lib.lib().fc_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), c_int(B), c_int(N), c_int(H),
+    rc = _lib.lib().fc_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dbias), c_int(B), c_int(N), c_int(H),
                                      c_int(64), c_int(_dev(qkv)), _st(qkv))
     _lib.check(rc, "fc_attention_bwd")
     return dqkv
@@ -68,12 +68,12 @@ def layernorm_fwd(x, gamma, beta, eps, bf16_out=True):
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dxs=None, row_scale=None, rows_per_group=0,
-                  dgamma=None, dbeta=None):
+                  dgamma=None, dbeta=None, dxs_colsum=None):
     rows, d = x.shape
     rc = _lib.lib().fc_layernorm_bwd(ptr(dy), c_int(int(dy.dtype == torch.bfloat16)), c_ll(dy.stride(0)), ptr(x),
                                      c_ll(x.stride(0)), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), c_ll(dx.stride(0)),
                                      c_int(int(accumulate)), ptr(dxs), c_ll(dxs.stride(0) if dxs is not None else d),
-                                     ptr(row_scale), c_int(rows_per_group), ptr(dgamma), ptr(dbeta), c_int(rows),
+                                     ptr(row_scale), c_int(rows_per_group), ptr(dgamma), ptr(dbeta), ptr(dxs_colsum), c_int(rows),
                                      c_int(d), c_int(_dev(x)), _st(x))
     _lib.check(rc, "fc_layernorm_bwd")
     return dx

@@ -184,7 +184,7 @@ class FedavgServer(BaseServer):
         self._owner = {}
         for i, cid in enumerate(sampled_client_ids):
             self.clients[cid].device = self._client_device(i)
-            self._owner[cid] = i % self.world_size
+            self._owner[cid] = agg.shard_owner(i, self.world_size)
         return sampled_client_ids
 
     # ---- logging (:314-400) ----------------------------------------------------------------------------
@@ -323,20 +323,8 @@ class FedavgServer(BaseServer):
                 ev1.record()
             else:
                 # closed-form partial sums per rank + one all-reduce over NVLink (not bit-exact: <= 1e-6 rel)
-                parts = []
-                for g in gl:
-                    part = g.arena_in.clone() if self.rank == 0 else torch.zeros_like(g.arena_in)
-                    g.arena_out = part
-                    parts.append(part)
-                plan = agg.AggregationPlan(gl, cl, self.param_scope, mode=agg.WSUM,
-                                           include_global_term=(self.rank == 0), **flags).to_device(self.server_device)
                 ev0.record()
-                plan.launch()
-                works = [d.all_reduce(p, op=d.ReduceOp.SUM, async_op=True) for p in parts]
-                for w in works:
-                    w.wait()
-                for g, p in zip(gl, parts):
-                    g.arena_in.copy_(p)
+                plan = agg.sharded_aggregate(gl, cl, self.param_scope, flags, d, self.rank)
                 ev1.record()
         self.last_aggregation = dict(events=(ev0, ev1), bytes=plan.algorithmic_bytes, jobs=plan.n_jobs,
                                      tiles=plan.n_tiles, plan=plan)

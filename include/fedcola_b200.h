@@ -66,9 +66,9 @@ int fc_aggregate(int mode, int n_jobs, int n_tiles, const int* job_tile_start,
  *   a_mn_major / b_mn_major = 1: the operand is stored [K, rows] (rows contiguous) instead of [rows, K].
  * ------------------------------------------------------------------------------------------------ */
 #define FC_EPI_BF16 0        /* out(bf16) = acc + bias                                              */
-#define FC_EPI_GELU 1        /* out(bf16) = acc + bias ; out2(bf16) = gelu_erf(acc + bias)          */
+#define FC_EPI_GELU 1        /* x = acc + bias: out(bf16) = gelu_erf'(x) ; out2(bf16) = gelu_erf(x)  */
 #define FC_EPI_RESID 2       /* out(f32)  = resid + row_scale[row/rows_per_group] * (acc + bias)    */
-#define FC_EPI_DGELU 3       /* out(bf16) = acc * gelu_erf'(aux)     (aux = bf16 pre-activation)    */
+#define FC_EPI_MULAUX 3      /* out(bf16) = acc * aux (aux = bf16, e.g. the saved gelu'); colsum += column sums */
 #define FC_EPI_F32 4         /* out(f32)  = acc + bias                                              */
 #define FC_EPI_ATOMIC_F32 5  /* out(f32) += alpha * acc  (red.add; split-K; splits <= 0 = choose automatically) */
 #define FC_EPI_PATCH 6       /* out(f32)[b*(P+1)+1+t] = acc + bias + pos[1+t]  (row = b*P + t)      */
@@ -76,8 +76,8 @@ int fc_aggregate(int mode, int n_jobs, int n_tiles, const int* job_tile_start,
 int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
                  long long ldb, int b_mn_major, int epi, void* out, void* out2, long long ldo,
                  const float* bias, const float* resid, const float* row_scale, int rows_per_group,
-                 const void* aux, const float* pos, int patches, float alpha, int splits, int device,
-                 void* stream);
+                 const void* aux, const float* pos, int patches, float alpha, int splits, float* colsum,
+                 int device, void* stream);
 
 /* Per-launch GEMM timing with CUDA events on the launching stream (measurement aid; off by default). */
 void fc_gemm_profile(int enable);
@@ -90,14 +90,16 @@ long long fc_gemm_profile_collect(double* total_ms, double* total_flops);
  * ------------------------------------------------------------------------------------------------ */
 int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim, int device,
                      void* stream);
-int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B,
-                     int N, int H, int head_dim, int device, void* stream);
+/* dbias (nullable): fp32 [3*H*64] += column sums of dqkv (the qkv bias gradient) */
+int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
+                     float* dbias, int B, int N, int H, int head_dim, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the fp32 residual stream           ref: src/models/mome.py:203,215,226-227,751-752
  *   fwd: y = LN(x) as bf16 (GEMM operand) and/or fp32; mean/rstd saved per row.
  *   bwd: dx (+)= LN'(dy); optional bf16 copy dxs = row_scale[row/rows_per_group] * dx for the next
- *        backward GEMM; dgamma/dbeta accumulated with atomics.
+ *        backward GEMM; dgamma/dbeta accumulated with atomics; dxs_colsum (nullable) += column sums of dxs
+ *        (the bias gradient of the Linear that consumes dxs).
  * ------------------------------------------------------------------------------------------------ */
 int fc_layernorm_fwd(const float* x, long long x_row_stride, const float* gamma, const float* beta, float eps,
                      void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int d, int device,
@@ -106,7 +108,7 @@ int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row_stride, co
                      long long x_row_stride, const float* mean, const float* rstd, const float* gamma,
                      float* dx, long long dx_row_stride, int accumulate, void* dxs_bf16,
                      long long dxs_row_stride, const float* row_scale, int rows_per_group, float* dgamma,
-                     float* dbeta, int rows, int d, int device, void* stream);
+                     float* dbeta, float* dxs_colsum, int rows, int d, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embeddings / heads / losses        ref: src/models/mome.py:597-611 (image), :632-639 (text, BertEmbeddings),

@@ -65,26 +65,58 @@ def test_tn_split_k_atomic(splits, cuda):
 
 
 def test_gelu_epilogue(cuda):
+    """fc1 forward: out = gelu'(x) (saved for the backward), out2 = gelu(x), x = A W^T + b (exact-erf GELU)."""
     M, N, K = 500, 1536, 384
     A, B = _mk(M, K, cuda, 9, 0.5), _mk(N, K, cuda, 10, 0.1)
     bias = torch.randn(N, device=cuda) * 0.1
-    pre = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
-    act = torch.zeros_like(pre)
-    ops.gemm_bf16(A, B, ops.EPI_GELU, pre, out2=act, bias=bias)
-    ref = A.float() @ B.float().t() + bias
-    _close(pre, ref, 2 ** -7, 1e-2)
-    _close(act, F.gelu(ref), 2 ** -7, 1e-2)
+    dact = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+    act = torch.zeros_like(dact)
+    ops.gemm_bf16(A, B, ops.EPI_GELU, dact, out2=act, bias=bias)
+    ref = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    y = F.gelu(ref)
+    y.sum().backward()
+    _close(act, y.detach(), 2 ** -7, 1e-2)
+    _close(dact, ref.grad, 2 ** -7, 1e-2)
 
 
-def test_dgelu_epilogue(cuda):
+def test_gelu_matches_exact_erf_over_range(cuda):
+    """The rational erf of the epilogue against torch's exact-erf GELU and its derivative on [-12, 12]:
+    acc[m, n] = A[m, 0] * B[n, 0] = x_n for every row."""
+    M, N, K = 128, 1024, 64
+    A = torch.zeros(M, K, device=cuda, dtype=torch.bfloat16)
+    B = torch.zeros(N, K, device=cuda, dtype=torch.bfloat16)
+    A[:, 0] = 1.0
+    B[:, 0] = torch.linspace(-12, 12, N, device=cuda).to(torch.bfloat16)
+    dact = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+    act = torch.zeros_like(dact)
+    ops.gemm_bf16(A, B, ops.EPI_GELU, dact, out2=act)
+    x = B[:, 0].float().requires_grad_(True)
+    y = F.gelu(x)
+    y.sum().backward()
+    for r in (0, M - 1):
+        _close(act[r], y.detach(), 2 ** -8, 1e-6)
+        _close(dact[r], x.grad, 2 ** -8, 1e-6)
+
+
+def test_mulaux_epilogue_with_bias_grad(cuda):
+    """fc2 backward: d_h = (dY W2) * gelu'(pre) with the fc1 bias gradient (column sums of d_h) fused."""
     M, N, K = 300, 1536, 384
     A, B = _mk(M, K, cuda, 11, 0.5), _mk(N, K, cuda, 12, 0.1)
-    pre = _mk(M, N, cuda, 13)
+    aux = _mk(M, N, cuda, 13)
     out = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
-    ops.gemm_bf16(A, B, ops.EPI_DGELU, out, aux=pre)
-    x = pre.float().requires_grad_(True)
-    F.gelu(x).sum().backward()
-    _close(out, (A.float() @ B.float().t()) * x.grad, 2 ** -7, 1e-2)
+    colsum = torch.ones(N, device=cuda)
+    ops.gemm_bf16(A, B, ops.EPI_MULAUX, out, aux=aux, colsum=colsum)
+    ref = (A.float() @ B.float().t()) * aux.float()
+    _close(out, ref, 2 ** -7, 1e-2)
+    _close(colsum, 1.0 + out.float().sum(0), 1e-4, 1e-3)          # sums the bf16 values actually stored
+    # MN-major B (the layout the driver uses: W2 is [d, 4d]) and a ragged N
+    Bt = _mk(K, 200, cuda, 14, 0.1)
+    aux2 = _mk(M, 200, cuda, 15)
+    out2 = torch.zeros(M, 200, device=cuda, dtype=torch.bfloat16)
+    cs2 = torch.zeros(200, device=cuda)
+    ops.gemm_bf16(A, Bt, ops.EPI_MULAUX, out2, b_mn=True, aux=aux2, colsum=cs2)
+    _close(out2, (A.float() @ Bt.float()) * aux2.float(), 2 ** -7, 1e-2)
+    _close(cs2, out2.float().sum(0), 1e-4, 1e-3)
 
 
 def test_residual_droppath_epilogue(cuda):

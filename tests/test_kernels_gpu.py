@@ -44,7 +44,9 @@ def test_attention_backward(B, N, H, cuda):
     qkv = torch.randn(B, N, 3, H, 64, device=cuda).to(torch.bfloat16)
     dout = (torch.randn(B, N, H * 64, device=cuda) * 0.1).to(torch.bfloat16)
     out, lse = ops.attention_fwd(qkv, B, N, H)
-    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H)
+    dbias = torch.ones(3 * H * 64, device=cuda)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, dbias=dbias)
+    _close(dbias, 1.0 + dqkv.float().view(B * N, 3 * H * 64).sum(0), 1e-3, 2e-3, "fused qkv bias gradient")
     x = qkv.float().requires_grad_(True)
     q, k, v = x.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
     o = (((q * 0.125) @ k.transpose(-2, -1)).softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * 64)
@@ -78,8 +80,10 @@ def test_layernorm_forward_backward(rows, d, eps, cuda):
     scale = torch.rand((rows + group - 1) // group, device=cuda) + 0.5
     dxs = torch.empty(rows, d, dtype=torch.bfloat16, device=cuda)
     dgamma, dbeta = torch.zeros(d, device=cuda), torch.zeros(d, device=cuda)
+    colsum = torch.full((d,), 2.0, device=cuda)
     ops.layernorm_bwd(dy, x, mean, rstd, g, dx, True, dxs=dxs, row_scale=scale, rows_per_group=group, dgamma=dgamma,
-                      dbeta=dbeta)
+                      dbeta=dbeta, dxs_colsum=colsum)
+    _close(colsum, 2.0 + dxs.float().sum(0), 1e-4, 1e-3 * rows ** 0.5, "fused bias gradient (colsum of dxs)")
     _close(dx, dx0 + xr.grad, 1e-4, 1e-4, "ln bwd dx")
     _close(dxs, (dx0 + xr.grad) * scale.repeat_interleave(group)[:rows, None], 2 ** -8, 1e-3, "ln bwd dxs")
     _close(dgamma, gr.grad, 1e-3, 1e-3 * rows ** 0.5, "dgamma")

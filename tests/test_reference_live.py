@@ -1,0 +1,49 @@
+"""Runs only where the unmodified reference exists (/root/reference, this container): checks that the golden
+fixtures are what the reference produces NOW (guards against stale fixtures), and pins the model mirror's
+key layout and seeded initialisation against the reference constructor."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference not present")]
+
+
+def test_aggregation_golden_is_fresh():
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import make_golden
+    import helpers as H
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "agg_hashes.json")))
+    for case in ("fedcola_attn_modality_comp_aux", "modality_exact_comp"):
+        res = make_golden.reference_aggregate(case)
+        assert {ds: {k: H.sha(v) for k, v in sd.items()} for ds, sd in res.items()} == gold[case]
+
+
+def test_mirror_init_and_keys_match_reference():
+    import timm
+    from oracle import ref_shim
+    ref_shim.install()
+    from fedcola_b200.harness import make_args
+    from fedcola_b200.models import mome as our
+    for scope in ("modality", "all"):
+        for aux in (False, True):
+            for mods, ncls, tasks in ((["img", None], [100, None], ["cls", None]), ([None, "txt"], [None, 4], [None, "cls"]),
+                                      (["img", "txt"], [None, None], ["rtv", "rtv"])):
+                args = make_args(shared_param="attn", share_scope=scope, vocab_size=512, seq_len=16)
+                kw = dict(pretrained=False, num_classes=ncls, modalities=mods, args=args, tasks=tasks, with_aux=aux,
+                          aux_trained=False, aux_attn_only=False, aux_mlp_only=False)
+                torch.manual_seed(3)
+                ref = timm.create_model("mome_d64_l2", **kw)
+                torch.manual_seed(3)
+                mine = our.create_model("mome_d64_l2", **kw)
+                a, b = ref.state_dict(), mine.state_dict()
+                assert list(a.keys()) == list(b.keys())
+                assert all(torch.equal(a[k], b[k]) for k in a)
+                assert [(k, p.requires_grad) for k, p in ref.named_parameters()] == \
+                       [(k, p.requires_grad) for k, p in mine.named_parameters()]
+                assert list(ref.required_params().keys()) == list(mine.required_params().keys())

@@ -58,7 +58,7 @@ run("fwd fc1   [T,384]x[1536,384] gelu", lambda: ops.gemm_bf16(x, W1, ops.EPI_GE
     2 * T * 4 * d * d, T * d * 2 + 2 * T * 4 * d * 2)
 run("fwd fc2   [T,1536]x[384,1536] resid", lambda: ops.gemm_bf16(h, W2, ops.EPI_RESID, of, bias=b1, resid=res),
     2 * T * 4 * d * d, T * 4 * d * 2 + 2 * T * d * 4)
-run("bwd dX fc2 [T,384]x[384,1536]mn dgelu", lambda: ops.gemm_bf16(x, W2, ops.EPI_DGELU, o4a, b_mn=True, aux=o4b),
+run("bwd dX fc2 [T,384]x[384,1536]mn mulaux+colsum", lambda: ops.gemm_bf16(x, W2, ops.EPI_MULAUX, o4a, b_mn=True, aux=o4b, colsum=b4),
     2 * T * 4 * d * d, T * d * 2 + 2 * T * 4 * d * 2)
 run("bwd dX fc1 [T,1536]x[1536,384]mn", lambda: ops.gemm_bf16(h, W1, ops.EPI_BF16, o1, b_mn=True),
     2 * T * 4 * d * d, T * 4 * d * 2 + T * d * 2)
