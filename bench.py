@@ -159,6 +159,7 @@ def run_ours(a):
                 for k in phases:
                     phases[k] += server.phase_ms[k] / steps
         timed_rounds.phases = phases
+        timed_rounds.per_round = [round(x, 1) for x in per]
         t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -178,7 +179,7 @@ def run_ours(a):
 
     # ---- kernel-side number: client data resident in HBM ---------------------------------------------
     server, args = make_server("device")
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("FC_BENCH_NO_CLOCKS")) else None
     l0 = L.fc_launch_count()
     total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, a.warmup, sampler)
     launches = (L.fc_launch_count() - l0)
@@ -186,6 +187,7 @@ def run_ours(a):
     launches_timed = int(launches * a.steps / (a.steps + a.warmup))
     value = samples / (total_ms / 1e3)
     phases = dict(timed_rounds.phases)
+    per_round_ms = list(timed_rounds.per_round)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): one extra round with per-launch CUDA events ----
     L.fc_gemm_profile(1)
@@ -233,6 +235,7 @@ def run_ours(a):
                          "launches_per_round": int(n_gemm), "avg_launch_us": round(ms.value * 1e3 / max(n_gemm, 1), 2),
                          "round_model_tflops": round(round_flops * n_gpus / (total_ms / a.steps * 1e-3) / 1e12 / n_gpus, 2)},
             "phase_ms_host_clock": {k: round(v, 2) for k, v in phases.items()},
+            "per_round_ms": per_round_ms, "e2e_per_round_ms": list(timed_rounds.per_round),
             "train_phase_samples_per_s": round(samples / a.steps / (phases["local_training"] * 1e-3), 2),
             "aggregation": {"gbs": round(agg_best, 1), "frac_of_measured_hbm": round(agg_best / pk["hbm"], 4),
                             "bytes_per_round": int(agg_bytes[0]) if agg_bytes else 0,

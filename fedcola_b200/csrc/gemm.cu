@@ -3,23 +3,26 @@
 // Replaces the cuBLAS sgemm calls behind every nn.Linear / CrossModalReparamLinear of the reference's
 // Block (/root/reference/src/models/mome.py:58-60,112-121,143-166) and the PatchEmbed conv (:252-265),
 // forward and backward, with the elementwise work that follows each of them fused into the epilogue:
-//   bias, exact-erf GELU (value + derivative in one pass), multiply-by-saved-derivative (+ bias-gradient column sums), DropPath-scaled residual add, patch-row remap + pos_embed,
-//   split-K gradient accumulation.
+//   bias, exact-erf GELU (value + derivative in one pass), multiply-by-saved-derivative (+ bias-gradient
+//   column sums), DropPath-scaled residual add, patch-row remap + pos_embed, split-K gradient accumulation.
 //
 // Persistent, warp-specialised kernel: one CTA per SM walks 128 x BN output tiles (BN = 128 / 192 / 256,
-// UMMA M=128, N=BN, K=16 per instruction).  A 4-6 stage TMA->smem ring of 64-wide K blocks (128-byte
+// UMMA M=128, N=BN, K=16 per instruction).  A 3-5 stage TMA->smem ring of 64-wide K blocks (128-byte
 // swizzle) runs across tile boundaries; the fp32 accumulator is double-buffered in TMEM (2 x 256 columns)
-// so the 12 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
-// K = 384..1536: short main loops, store-heavy epilogues.  The epilogue transposes each 32x32 accumulator
-// block through shared memory so that every global load/store of a warp covers whole 64/128-byte row
-// segments (resid / pre-activation reads and all writes are coalesced).
+// so the 16 epilogue warps drain tile i while the MMA warp already works on tile i+1 — these GEMMs have
+// K = 384..1536: short main loops, store-heavy epilogues.  The epilogue (the measured bottleneck: it is
+// instruction-issue bound) is specialised per fused op at compile time, transposes each 32x32 accumulator
+// block through shared memory (two 16-row passes) so that every global load/store of a warp covers whole
+// 64/128-byte row segments, and issues the global loads it needs (bias, residual, saved gelu') before the
+// TMEM load so that their latency overlaps it.
 //
 // Operand majors: A and B may each be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows
-// contiguous) — the latter serves dW = dY^T X without materialising any transpose.
+// contiguous) — the latter serves dX = dY W and dW = dY^T X without materialising any transpose.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "../../include/fedcola_b200.h"
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -29,17 +32,18 @@ using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 12;              // three warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int EPI_WARPS = 16;              // four warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 constexpr int STAGE_LD = 36;               // floats per row of the epilogue transpose buffer (144 B: conflict-free)
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 16 * STAGE_LD * 4;   // per warp: 16 rows x 32 columns per pass
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
 template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);   // what fits beside the epilogue staging
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
 struct GemmParams {
@@ -59,11 +63,12 @@ struct GemmParams {
   const float* pos;         // EPI_PATCH: pos_embed [(P+1), N]
   int patches;              // EPI_PATCH: P (196)
   float alpha;
+  int debug;                // measurement aid (FC_GEMM_DEBUG env): 1 = skip epilogue work, 2 = skip TMA+MMA work
 };
 
 // Exact-erf GELU (nn.GELU() default) evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf
 // (|error| <= 1.5e-7, far below the bf16 rounding of the stored result): one MUFU.RCP + one MUFU.EX2 + 6 FMAs
-// instead of erff's ~30-instruction polynomial — the GELU epilogues are ALU-bound otherwise.
+// instead of erff's ~30-instruction polynomial.
 //   Phi(x) = 0.5*(1 + erf(x/sqrt2));  with z = |x|/sqrt2, t = 1/(1 + p z):  1 - erf(z) = poly(t) * exp(-z^2)
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
@@ -77,173 +82,181 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
   const float tail = 0.5f * t * poly * e;                         // = 0.5*(1 - erf(z)) = Phi(-|x|), no cancellation
   cdf = x >= 0.0f ? 1.0f - tail : tail;
 }
-__device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);               // Phi(x) + x*phi(x)
-}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// explicit shared-state-space accesses (32-bit addresses): the transpose buffer must not go through generic LD/ST
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Epilogue of one 32x32 accumulator block that sits transposed in `stage` (row-major, STAGE_LD floats per
-// row).  Lane l owns columns col..col+3 (col = col0 + 4*(l&7)) of rows r_i = (l>>3) + 4*i, i = 0..7: every
-// global access of the warp covers 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.  All global LOADS
-// of a block are issued before the first dependent use, so their latency is paid once per block.
-__device__ __forceinline__ void epilogue_block(const GemmParams& p, const float* stage, int row_base, int col0, int lane) {
-  const int rsub = lane >> 3, col = col0 + (lane & 7) * 4;
-  if (col >= p.N && p.colsum == nullptr) return;   // N is a multiple of 8, col a multiple of 4
-  const bool col_ok = col < p.N;                 // (with colsum the whole warp stays for the shuffles)
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-  float4 v[8];
+// Operands the epilogue reads from global memory (residual rows / saved gelu'), fetched for a whole 32x32
+// chunk (both 16-row passes) BEFORE the TMEM load + transpose so that their latency overlaps that work.
+// Entry 4*h + j belongs to row  row_base + (lane>>3) + 16*h + 4*j  (h = pass, j = 0..3).
+template <int EPI> struct EpiPre {};
+template <> struct EpiPre<FC_EPI_RESID> { float4 x[8]; float sc[8]; };
+template <> struct EpiPre<FC_EPI_MULAUX> { uint2 q[8]; };
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EPI>& pre, int row_base, int col0, int lane) {
+  const int col = col0 + (lane & 7) * 4;
+  const int r0 = row_base + (lane >> 3);
+  if constexpr (EPI == FC_EPI_RESID) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(stage + (rsub + 4 * i) * STAGE_LD + (lane & 7) * 4);
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + 4 * i;
+      pre.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre.sc[i] = 1.0f;
+      if (col < p.N && row < p.M) {
+        pre.x[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + col);
+        if (p.row_scale) pre.sc[i] = __ldg(p.row_scale + row / p.rows_per_group);
+      }
+    }
+  } else if constexpr (EPI == FC_EPI_MULAUX) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + 4 * i;
+      pre.q[i] = make_uint2(0u, 0u);
+      if (col < p.N && row < p.M) pre.q[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<size_t>(row) * p.ldo + col);
+    }
+  }
+}
+
+// Epilogue of one 16x32 accumulator block that sits transposed in `stage` (row-major, STAGE_LD floats per
+// row).  Lane l owns columns col..col+3 (col = col0 + 4*(l&7)) of rows r_i = (l>>3) + 4*i, i = 0..3: every
+// global access of the warp covers 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.
+// EPI is a compile-time constant: one lean instruction stream per fused op.  H = which 16-row pass.
+template <int EPI, int H>
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t stage, int row_base, int col0, int lane,
+                                               float4 bias, const EpiPre<EPI>& pre) {
+  const int rsub = lane >> 3, col = col0 + (lane & 7) * 4;
+  const bool col_ok = col < p.N;                 // N is a multiple of 8, col a multiple of 4
+  if (EPI != FC_EPI_MULAUX && !col_ok) return;   // (MULAUX keeps the whole warp for the colsum shuffles)
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = lds_v4(stage + ((rsub + 4 * i) * STAGE_LD + (lane & 7) * 4) * 4);
     v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w;
   }
-  const int r0 = row_base + rsub;
-#define ROW(i) (col_ok ? r0 + 4 * (i) : p.M)
-#define OFF(i) (static_cast<size_t>(ROW(i)) * p.ldo + col)
-  switch (p.epi) {
-    case FC_EPI_BF16: {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int r0 = row_base + H * 16 + rsub;
+  bool ok[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M)
-          *reinterpret_cast<uint2*>(out + OFF(i)) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
-    } break;
-    case FC_EPI_GELU: {
-      // out = gelu'(pre) (what the backward needs), out2 = gelu(pre) (the fc2 operand); Phi and exp are shared
-      __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out);
-      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2);
+  for (int i = 0; i < 4; ++i) ok[i] = col_ok && (r0 + 4 * i < p.M);
+  const size_t o0 = static_cast<size_t>(r0) * p.ldo + col;
+  const size_t rstep = static_cast<size_t>(4) * p.ldo;
+
+  if constexpr (EPI == FC_EPI_BF16) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M) {
-          float g[4], d[4];
-          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) *reinterpret_cast<uint2*>(out + i * rstep) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+  } else if constexpr (EPI == FC_EPI_GELU) {
+    // out = gelu'(pre) (what the backward needs), out2 = gelu(pre) (the fc2 operand); Phi and exp are shared
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + o0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float cdf, e;
-            gelu_parts(x[k], cdf, e);
-            g[k] = x[k] * cdf;
-            d[k] = fmaf(x[k] * 0.39894228040143267794f, e, cdf);
-          }
-          *reinterpret_cast<uint2*>(o1 + OFF(i)) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
-          *reinterpret_cast<uint2*>(o2 + OFF(i)) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) {
+        float g[4], d[4];
+        const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float cdf, e;
+          gelu_parts(x[k], cdf, e);
+          g[k] = x[k] * cdf;
+          d[k] = fmaf(x[k] * 0.39894228040143267794f, e, cdf);     // Phi(x) + x*phi(x)
         }
-    } break;
-    case FC_EPI_RESID: {
-      float4 x[8];
-      float sc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sc[i] = 1.0f;
-        if (ROW(i) < p.M) {
-          x[i] = *reinterpret_cast<const float4*>(p.resid + OFF(i));
-          if (p.row_scale) sc[i] = __ldg(p.row_scale + ROW(i) / p.rows_per_group);
-        }
+        *reinterpret_cast<uint2*>(o1 + i * rstep) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
+        *reinterpret_cast<uint2*>(o2 + i * rstep) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
       }
-      float* out = reinterpret_cast<float*>(p.out);
+  } else if constexpr (EPI == FC_EPI_RESID) {
+    float* out = reinterpret_cast<float*>(p.out) + o0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M)
-          *reinterpret_cast<float4*>(out + OFF(i)) = make_float4(x[i].x + sc[i] * v[i].x, x[i].y + sc[i] * v[i].y,
-                                                                 x[i].z + sc[i] * v[i].z, x[i].w + sc[i] * v[i].w);
-    } break;
-    case FC_EPI_MULAUX: {
-      uint2 q[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        q[i] = make_uint2(0u, 0u);
-        if (ROW(i) < p.M) q[i] = *reinterpret_cast<const uint2*>(p.aux + OFF(i));
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) {
+        const float4 x = pre.x[H * 4 + i];
+        const float sc = pre.sc[H * 4 + i];
+        *reinterpret_cast<float4*>(out + i * rstep) =
+            make_float4(x.x + sc * v[i].x, x.y + sc * v[i].y, x.z + sc * v[i].z, x.w + sc * v[i].w);
       }
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if constexpr (EPI == FC_EPI_MULAUX) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M) {
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[i].y));
-          const uint32_t w0 = pack_bf16(v[i].x * lo.x, v[i].y * lo.y), w1 = pack_bf16(v[i].z * hi.x, v[i].w * hi.y);
-          *reinterpret_cast<uint2*>(out + OFF(i)) = make_uint2(w0, w1);
-          if (p.colsum != nullptr) {      // sum what was actually stored (bf16-rounded), as a separate pass would
-            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
-            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
-            cs.x += a.x; cs.y += a.y; cs.z += b.x; cs.w += b.y;
-          }
-        }
-      if (p.colsum != nullptr) {          // 32 rows of this block: lanes l, l+8, l+16, l+24 share the columns
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-        }
-        if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs.x, cs.y, cs.z, cs.w);
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) {
+        const uint2 q = pre.q[H * 4 + i];
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+        const uint32_t w0 = pack_bf16(v[i].x * lo.x, v[i].y * lo.y), w1 = pack_bf16(v[i].z * hi.x, v[i].w * hi.y);
+        *reinterpret_cast<uint2*>(out + i * rstep) = make_uint2(w0, w1);
+        // sum what was actually stored (bf16-rounded), as a separate column-sum pass over the output would
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+        cs.x += a.x; cs.y += a.y; cs.z += b.x; cs.w += b.y;
       }
-    } break;
-    case FC_EPI_F32: {
-      float* out = reinterpret_cast<float*>(p.out);
+    if (p.colsum != nullptr) {            // 16 rows of this block: lanes l, l+8, l+16, l+24 share the columns
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M) *reinterpret_cast<float4*>(out + OFF(i)) = v[i];
-    } break;
-    case FC_EPI_ATOMIC_F32: {
-      float* out = reinterpret_cast<float*>(p.out);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M)
-          red_add_v4(out + OFF(i), p.alpha * v[i].x, p.alpha * v[i].y, p.alpha * v[i].z, p.alpha * v[i].w);
-    } break;
-    case FC_EPI_PATCH: {
-      // row = b*P + t  ->  token row b*(P+1) + 1 + t of x; add pos_embed[1+t]
-      float4 e[8];
-      int orow[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        orow[i] = 0;
-        if (ROW(i) < p.M) {
-          const int b = ROW(i) / p.patches, t = ROW(i) - b * p.patches;
-          orow[i] = b * (p.patches + 1) + 1 + t;
-          e[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
-        }
+      for (int o = 8; o <= 16; o <<= 1) {
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
       }
-      float* out = reinterpret_cast<float*>(p.out);
+      if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs.x, cs.y, cs.z, cs.w);
+    }
+  } else if constexpr (EPI == FC_EPI_F32) {
+    float* out = reinterpret_cast<float*>(p.out) + o0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ROW(i) < p.M)
-          *reinterpret_cast<float4*>(out + static_cast<size_t>(orow[i]) * p.ldo + col) =
-              make_float4(v[i].x + e[i].x, v[i].y + e[i].y, v[i].z + e[i].z, v[i].w + e[i].w);
-    } break;
-    default: break;
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) *reinterpret_cast<float4*>(out + i * rstep) = v[i];
+  } else if constexpr (EPI == FC_EPI_ATOMIC_F32) {
+    float* out = reinterpret_cast<float*>(p.out) + o0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (ok[i]) red_add_v4(out + i * rstep, p.alpha * v[i].x, p.alpha * v[i].y, p.alpha * v[i].z, p.alpha * v[i].w);
+  } else if constexpr (EPI == FC_EPI_PATCH) {
+    // row = b*P + t  ->  token row b*(P+1) + 1 + t of x; add pos_embed[1+t]
+    float4 e[4];
+    int orow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      orow[i] = 0;
+      if (ok[i]) {
+        const int row = r0 + 4 * i, b = row / p.patches, t = row - b * p.patches;
+        orow[i] = b * (p.patches + 1) + 1 + t;
+        e[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
+      }
+    }
+    float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (ok[i])
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(orow[i]) * p.ldo + col) =
+            make_float4(v[i].x + e[i].x, v[i].y + e[i].y, v[i].z + e[i].z, v[i].w + e[i].w);
   }
-#undef ROW
-#undef OFF
 }
 
 // Persistent, warp-specialised: each CTA (one per SM) walks tiles  t = blockIdx.x, +gridDim.x, ...
 //   tile -> (split, m_blk, n_blk), n fastest so CTAs running side by side share the A rows in L2.
 // smem ring (TMA -> MMA) runs across tile boundaries; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
@@ -281,7 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && !(p.debug & 2)) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -322,6 +335,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_COLS;
+        if (p.debug & 2) {                     // measurement aid: no operands, no MMAs — epilogue-only timing
+          mbar_arrive(&tmem_full_bar[buf]);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -344,10 +361,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    constexpr int WPQ = EPI_WARPS / 4;         // warps per lane quarter
-    const int half = (warp - 2) >> 2;          // which warp of that quarter: chunks c = half, half + WPQ, ...
-    float* stage = epi_stage + (warp - 2) * (32 * STAGE_LD);
+    constexpr int WPQ = EPI_WARPS / 4;         // warps per TMEM lane quarter
+    const int q = warp & 3;                    // lane quarter this warp may access
+    const int sub = (warp - 2) >> 2;           // which warp of that quarter: chunks c = sub, sub + WPQ, ...
+    const uint32_t stage = smem_u32(epi_stage) + (warp - 2) * (16 * STAGE_LD * 4);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % tiles_mn;
@@ -356,16 +373,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
-      // chunks this warp owns: c = half, half+2, ... ; the last one it will actually read (col0 < N)
+      // chunks this warp owns: c = sub, sub+WPQ, ... ; the last one it will actually read (col0 < N)
       int last_c = -1;
-      for (int c = half; c < BN / 32; c += WPQ)
+      for (int c = sub; c < BN / 32; c += WPQ)
         if (n0 + c * 32 < p.N) last_c = c;
-      if (last_c < 0) {                        // nothing to read in this tile: release immediately
+      if (last_c < 0 || (p.debug & 1)) {       // nothing to read in this tile (or main-loop-only timing)
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        continue;
       }
 #pragma unroll 1
-      for (int c = half; c <= last_c; c += WPQ) {
+      for (int c = sub; c <= last_c; c += WPQ) {
+        const int col0 = n0 + c * 32;
+        // global operands of this chunk first: their latency overlaps the TMEM load and the transposes
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int bcol = col0 + (lane & 7) * 4;
+        if (p.bias != nullptr && bcol < p.N) bias = __ldg(reinterpret_cast<const float4*>(p.bias + bcol));
+        EpiPre<EPI> pre;
+        epilogue_prefetch<EPI>(p, pre, m0 + q * 32, col0, lane);
         float acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
@@ -374,13 +399,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
-        // transpose through smem: thread = row  ->  8 lanes per row, 4 columns each
+        // transpose through smem, 16 rows per pass: thread = row  ->  8 lanes per row, 4 columns each
+        if (lane < 16) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stage + lane * STAGE_LD + j * 4) =
-              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            sts_v4(stage + (lane * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
         __syncwarp();
-        epilogue_block(p, stage, m0 + q * 32, n0 + c * 32, lane);
+        epilogue_block<EPI, 0>(p, stage, m0 + q * 32, col0, lane, bias, pre);
+        __syncwarp();
+        if (lane >= 16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_v4(stage + ((lane - 16) * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2],
+                   acc[4 * j + 3]);
+        }
+        __syncwarp();
+        epilogue_block<EPI, 1>(p, stage, m0 + q * 32, col0, lane, bias, pre);
         __syncwarp();
       }
     }
@@ -432,9 +467,9 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 int g_prof_on = 0;
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device, cudaStream_t st) {
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   FC_SMEM_OPT_IN(kern, Cfg<BN>::SMEM_BYTES);
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = fc_num_sms(device);
@@ -456,13 +491,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   return FC_OK;
 }
 
+// Only the (operand majors x epilogue) combinations the round uses are instantiated:
+//   forward  A,B K-major        : BF16, GELU, RESID, F32, PATCH
+//   dX       A K-major, B MN    : BF16, MULAUX, F32
+//   dW       A,B MN-major       : ATOMIC_F32, F32
+//   (A MN, B K)                 : F32 (parity tests)
 template <int BN>
-int launch_majors(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int a_mn, int b_mn, int device,
-                  cudaStream_t st) {
-  if (a_mn && b_mn) return launch<BN, 1, 1>(ta, tb, p, device, st);
-  if (a_mn) return launch<BN, 1, 0>(ta, tb, p, device, st);
-  if (b_mn) return launch<BN, 0, 1>(ta, tb, p, device, st);
-  return launch<BN, 0, 0>(ta, tb, p, device, st);
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int a_mn, int b_mn, int device,
+              cudaStream_t st) {
+#define FC_CASE(AM, BMJ, E) \
+  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E>(ta, tb, p, device, st)
+  FC_CASE(0, 0, FC_EPI_BF16); FC_CASE(0, 0, FC_EPI_GELU); FC_CASE(0, 0, FC_EPI_RESID); FC_CASE(0, 0, FC_EPI_F32);
+  FC_CASE(0, 0, FC_EPI_PATCH);
+  FC_CASE(0, 1, FC_EPI_BF16); FC_CASE(0, 1, FC_EPI_MULAUX); FC_CASE(0, 1, FC_EPI_F32);
+  FC_CASE(1, 1, FC_EPI_ATOMIC_F32); FC_CASE(1, 1, FC_EPI_F32);
+  FC_CASE(1, 0, FC_EPI_F32);
+#undef FC_CASE
+  FC_FAIL(FC_ERR_UNSUPPORTED, "fc_gemm_bf16: epilogue %d is not built for operand majors (a_mn=%d, b_mn=%d)", p.epi,
+          a_mn, b_mn);
 }
 
 // Tile width: minimise (waves over the SMs) x (per-tile cost ~ BN + fixed overhead), i.e. trade the better
@@ -555,6 +601,10 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux); p.pos = pos; p.patches = patches; p.alpha = alpha;
   p.colsum = colsum;
+  {
+    static const int dbg = getenv("FC_GEMM_DEBUG") ? atoi(getenv("FC_GEMM_DEBUG")) : 0;
+    p.debug = dbg;
+  }
   CUtensorMap ta, tb;
   int rc;
   // K-major operand: global [rows, K]; MN-major operand: global [K, rows].
@@ -563,7 +613,7 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, bn);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_majors<256>(ta, tb, p, a_mn_major, b_mn_major, device, st);
-  if (bn == 192) return launch_majors<192>(ta, tb, p, a_mn_major, b_mn_major, device, st);
-  return launch_majors<128>(ta, tb, p, a_mn_major, b_mn_major, device, st);
+  if (bn == 256) return launch_bn<256>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  if (bn == 192) return launch_bn<192>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  return launch_bn<128>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
 }
