@@ -79,13 +79,18 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t_begin = None        # only samples taken after mark_begin() (the timed region) are reported
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                if self.t_begin is not None:
+                    self.rows.append([x.strip() for x in line.split(",")])
                 if self.stop_flag:
                     break
         except Exception:
@@ -138,7 +143,7 @@ def run_ours(a):
                 dist.barrier()
             torch.cuda.synchronize()
             if it == warmup and sampler is not None:
-                sampler.start()
+                sampler.mark_begin()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
@@ -180,6 +185,8 @@ def run_ours(a):
     # ---- kernel-side number: client data resident in HBM ---------------------------------------------
     server, args = make_server("device")
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("FC_BENCH_NO_CLOCKS")) else None
+    if sampler is not None:
+        sampler.start()        # spawn nvidia-smi now (forking this process mid-run costs ~0.3 s of host time)
     l0 = L.fc_launch_count()
     total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, a.warmup, sampler)
     launches = (L.fc_launch_count() - l0)

@@ -101,15 +101,15 @@ def test_gelu_matches_exact_erf_over_range(cuda):
 def test_mulaux_epilogue_with_bias_grad(cuda):
     """fc2 backward: d_h = (dY W2) * gelu'(pre) with the fc1 bias gradient (column sums of d_h) fused."""
     M, N, K = 300, 1536, 384
-    A, B = _mk(M, K, cuda, 11, 0.5), _mk(N, K, cuda, 12, 0.1)
+    A, B = _mk(M, K, cuda, 11, 0.5), _mk(K, N, cuda, 12, 0.1)       # B MN-major: W2 is stored [d, 4d]
     aux = _mk(M, N, cuda, 13)
     out = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
     colsum = torch.ones(N, device=cuda)
-    ops.gemm_bf16(A, B, ops.EPI_MULAUX, out, aux=aux, colsum=colsum)
-    ref = (A.float() @ B.float().t()) * aux.float()
+    ops.gemm_bf16(A, B, ops.EPI_MULAUX, out, b_mn=True, aux=aux, colsum=colsum)
+    ref = (A.float() @ B.float()) * aux.float()
     _close(out, ref, 2 ** -7, 1e-2)
     _close(colsum, 1.0 + out.float().sum(0), 1e-4, 1e-3)          # sums the bf16 values actually stored
-    # MN-major B (the layout the driver uses: W2 is [d, 4d]) and a ragged N
+    # ragged N (not a multiple of the 32-column epilogue chunk)
     Bt = _mk(K, 200, cuda, 14, 0.1)
     aux2 = _mk(M, 200, cuda, 15)
     out2 = torch.zeros(M, 200, device=cuda, dtype=torch.bfloat16)
@@ -146,3 +146,11 @@ def test_patch_epilogue(cuda):
     ref = (A.float() @ W.float().t() + bias).view(Bsz, P, d) + pos[1:]
     _close(out[:, 1:], ref, 1e-3, 1e-2)
     assert torch.count_nonzero(out[:, 0]) == 0
+
+
+def test_unbuilt_combination_is_refused(cuda):
+    """Only the (operand majors x epilogue) pairs the round uses are instantiated; others fail loudly."""
+    A, B = _mk(128, 64, cuda, 20), _mk(128, 64, cuda, 21)
+    out = torch.zeros(128, 128, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="not built"):
+        ops.gemm_bf16(A, B, ops.EPI_MULAUX, out, aux=out)
