@@ -108,6 +108,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    if int(os.environ.get("RANK", 0)) == 0:
+        sys.stderr.write(f"[bench +{time.time() - _T0:6.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_ours(a):
     import torch.distributed as dist
     from fedcola_b200 import _lib
@@ -117,8 +126,10 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))    # torchrun pins OMP_NUM_THREADS=1
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    _log("process group ready")
     n_gpus = max(world, 1)
     L = _lib.lib()
     L.fc_launch_count.restype = __import__("ctypes").c_ulonglong
@@ -184,12 +195,14 @@ def run_ours(a):
 
     # ---- kernel-side number: client data resident in HBM ---------------------------------------------
     server, args = make_server("device")
+    _log("server built (HBM-resident data)")
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("FC_BENCH_NO_CLOCKS")) else None
     if sampler is not None:
         sampler.start()        # spawn nvidia-smi now (forking this process mid-run costs ~0.3 s of host time)
     l0 = L.fc_launch_count()
     total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, a.warmup, sampler)
     launches = (L.fc_launch_count() - l0)
+    _log("timed rounds done")
     clocks = sampler.finish() if sampler is not None else None
     launches_timed = int(launches * a.steps / (a.steps + a.warmup))
     value = samples / (total_ms / 1e3)
@@ -214,12 +227,15 @@ def run_ours(a):
     # ---- end to end: same rounds, client data in pinned host memory (H2D per batch, D2H stats per epoch) ----
     del server
     torch.cuda.empty_cache()
+    _log("GEMM profile round done")
     server2, _ = make_server("host")
+    _log("server built (host-resident data)")
     e2e_ms, e2e_samples, _, _ = timed_rounds(server2, a.steps, max(a.warmup, 1))
     per_sample = {"img": 3 * 224 * 224 * 4 + 8, "txt": SEQ * 8 + 8, "img+txt": 3 * 224 * 224 * 4 + SEQ * 8}
     h2d = sum(per_sample[m] * N_PER_CLIENT * c for m, c in (("img", 3), ("txt", 3), ("img+txt", 2))) * n_gpus
     d2h = 16 * 8 * n_gpus
     e2e_value = e2e_samples / (e2e_ms / 1e3)
+    _log("e2e rounds done")
 
     if rank == 0:
         out = {

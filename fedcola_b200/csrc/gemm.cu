@@ -23,6 +23,7 @@
 #include "../../include/fedcola_b200.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -34,15 +35,16 @@ constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 16;              // four warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
-constexpr int STAGE_LD = 36;               // floats per row of the epilogue transpose buffer (144 B: conflict-free)
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 16 * STAGE_LD * 4;   // per warp: 16 rows x 32 columns per pass
+constexpr int STAGE_LD = 36;               // floats per row of the legacy transpose buffer (PATCH epilogue only)
+constexpr int EPI_BUF_BYTES = 32 * 128;    // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store/load tile)
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
 template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);   // what fits beside the epilogue staging
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
@@ -104,7 +106,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Entry 4*h + j belongs to row  row_base + (lane>>3) + 16*h + 4*j  (h = pass, j = 0..3).
 template <int EPI> struct EpiPre {};
 template <> struct EpiPre<FC_EPI_RESID> { float4 x[8]; float sc[8]; };
-template <> struct EpiPre<FC_EPI_MULAUX> { uint2 q[8]; };
+template <> struct EpiPre<FC_EPI_MULAUX> { uint2 q[8]; };   // (legacy register-prefetch path; PATCH is its only user now)
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EPI>& pre, int row_base, int col0, int lane) {
@@ -245,13 +247,164 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
   }
 }
 
+// ---- TMA-driven epilogue ------------------------------------------------------------------------------
+// Each epilogue warp owns a 32-row x 128-byte staging tile in shared memory, laid out exactly as a
+// SWIZZLE_128B TMA box: 16-byte chunk j of row t sits at  t*128 + ((j ^ (t & 7)) << 4).  A thread owns one
+// accumulator row (TMEM lane), so it writes its row straight into the tile (conflict-free thanks to the
+// swizzle); ONE thread then hands the tile to the TMA engine (cp.async.bulk.tensor store / reduce-add), which
+// does address generation, coalescing and M/N boundary clipping.  Residual / saved-gelu' operands arrive the same
+// way (TMA load into the tile, combined in place).  ~0.06 instructions per output element instead of ~0.4.
+__device__ __forceinline__ uint32_t swz128(uint32_t buf, int row, int chunk) {
+  return buf + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+
+template <int EPI> struct EpiTraits {
+  static constexpr bool kOut16 = (EPI == FC_EPI_BF16 || EPI == FC_EPI_GELU || EPI == FC_EPI_MULAUX);
+  static constexpr int kCW = kOut16 ? 64 : 32;      // columns per staging tile (128-byte rows either way)
+  static constexpr bool kLoads = (EPI == FC_EPI_RESID || EPI == FC_EPI_MULAUX);
+};
+
+// Store the staged tile: generic-proxy writes -> async proxy, one elected lane issues.  The store drains in the
+// background; stage_acquire() must be called before the staging buffer is written (or TMA-loaded) again.
+template <bool REDUCE>
+__device__ __forceinline__ void stage_store(const CUtensorMap* map, const void* buf_ptr, int col0, int row0, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (REDUCE) tma_reduce_add_2d(map, buf_ptr, col0, row0); else tma_store_2d(map, buf_ptr, col0, row0);
+    tma_store_commit();
+  }
+}
+__device__ __forceinline__ void stage_acquire(int lane) {
+  if (lane == 0) tma_store_wait_read();     // previous store of this warp has finished reading the buffer
+  __syncwarp();
+}
+
+// One 32-row x kCW-column chunk of the accumulator (acc[] = this lane's row) -> global, fused op EPI.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmO2,
+                                                   uint8_t* buf_ptr, uint32_t buf, uint64_t* ebar, uint32_t& eph,
+                                                   float (&acc)[EpiTraits<EPI>::kCW], int row0, int col0, int lane) {
+  constexpr int CW = EpiTraits<EPI>::kCW;
+  const int t = lane;
+  // bias: the same 4 columns for every lane -> uniform (broadcast) loads
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < CW / 4; ++j) {
+      if (col0 + 4 * j < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+        acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+      }
+    }
+  }
+  if constexpr (EPI == FC_EPI_BF16) {
+    stage_acquire(lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_u4(swz128(buf, t, j), pack_bf16(acc[8 * j], acc[8 * j + 1]), pack_bf16(acc[8 * j + 2], acc[8 * j + 3]),
+             pack_bf16(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16(acc[8 * j + 6], acc[8 * j + 7]));
+    stage_store<false>(tmO, buf_ptr, col0, row0, lane);
+  } else if constexpr (EPI == FC_EPI_GELU) {
+    // out = gelu'(x) (saved for the backward), out2 = gelu(x) (the fc2 operand); Phi and exp are shared
+    uint32_t gp[32];
+    stage_acquire(lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t dp[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float c0, e0, c1, e1;
+        const float x0 = acc[8 * j + 2 * k], x1 = acc[8 * j + 2 * k + 1];
+        gelu_parts(x0, c0, e0);
+        gelu_parts(x1, c1, e1);
+        gp[4 * j + k] = pack_bf16(x0 * c0, x1 * c1);
+        dp[k] = pack_bf16(fmaf(x0 * 0.39894228040143267794f, e0, c0), fmaf(x1 * 0.39894228040143267794f, e1, c1));
+      }
+      sts_u4(swz128(buf, t, j), dp[0], dp[1], dp[2], dp[3]);
+    }
+    stage_store<false>(tmO, buf_ptr, col0, row0, lane);
+    stage_acquire(lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts_u4(swz128(buf, t, j), gp[4 * j], gp[4 * j + 1], gp[4 * j + 2], gp[4 * j + 3]);
+    stage_store<false>(tmO2, buf_ptr, col0, row0, lane);
+  } else if constexpr (EPI == FC_EPI_RESID) {
+    const int row = row0 + t;
+    const float sc = (p.row_scale != nullptr && row < p.M) ? __ldg(p.row_scale + row / p.rows_per_group) : 1.0f;
+    mbar_wait(ebar, eph);                       // residual tile has landed in the staging buffer
+    eph ^= 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = swz128(buf, t, j);
+      const float4 x = lds_v4(a);
+      sts_v4(a, x.x + sc * acc[4 * j], x.y + sc * acc[4 * j + 1], x.z + sc * acc[4 * j + 2], x.w + sc * acc[4 * j + 3]);
+    }
+    stage_store<false>(tmO, buf_ptr, col0, row0, lane);
+  } else if constexpr (EPI == FC_EPI_MULAUX) {
+    mbar_wait(ebar, eph);                       // saved gelu' tile has landed
+    eph ^= 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = swz128(buf, t, j);
+      const uint4 q = lds_u4(a);
+      const float2 q0 = bf2_to_f2(q.x), q1 = bf2_to_f2(q.y), q2 = bf2_to_f2(q.z), q3 = bf2_to_f2(q.w);
+      sts_u4(a, pack_bf16(acc[8 * j] * q0.x, acc[8 * j + 1] * q0.y), pack_bf16(acc[8 * j + 2] * q1.x, acc[8 * j + 3] * q1.y),
+             pack_bf16(acc[8 * j + 4] * q2.x, acc[8 * j + 5] * q2.y), pack_bf16(acc[8 * j + 6] * q3.x, acc[8 * j + 7] * q3.y));
+    }
+    if (p.colsum != nullptr) {                  // bias gradient: column sums of the bf16 values just staged
+      __syncwarp();
+      float s0 = 0.f, s1 = 0.f;                 // lane owns columns 2*lane, 2*lane+1 of the tile
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float2 v = bf2_to_f2(lds_u32(swz128(buf, r, lane >> 2) + (lane & 3) * 4));
+        s0 += v.x;
+        s1 += v.y;
+      }
+      const int c = col0 + 2 * lane;
+      if (c < p.N) {
+        atomicAdd(p.colsum + c, s0);
+        atomicAdd(p.colsum + c + 1, s1);
+      }
+    }
+    stage_store<false>(tmO, buf_ptr, col0, row0, lane);
+  } else if constexpr (EPI == FC_EPI_F32) {
+    stage_acquire(lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts_v4(swz128(buf, t, j), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    stage_store<false>(tmO, buf_ptr, col0, row0, lane);
+  } else if constexpr (EPI == FC_EPI_ATOMIC_F32) {
+    stage_acquire(lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(swz128(buf, t, j), p.alpha * acc[4 * j], p.alpha * acc[4 * j + 1], p.alpha * acc[4 * j + 2], p.alpha * acc[4 * j + 3]);
+    stage_store<true>(tmO, buf_ptr, col0, row0, lane);     // cp.reduce.async.bulk .add.f32: split-K / grad accumulate
+  }
+}
+
 // Persistent, warp-specialised: each CTA (one per SM) walks tiles  t = blockIdx.x, +gridDim.x, ...
 //   tile -> (split, m_blk, n_blk), n fastest so CTAs running side by side share the A rows in L2.
 // smem ring (TMA -> MMA) runs across tile boundaries; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                 const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -261,7 +414,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* epi_bar = tmem_empty_bar + 2;            // [EPI_WARPS] one per epilogue warp (fused-operand TMA loads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = (p.K + BK - 1) / BK;
@@ -271,6 +425,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (EPI != FC_EPI_PATCH) prefetch_tmap(&tmO);
+    if (EPI == FC_EPI_GELU) prefetch_tmap(&tmO2);
+    if (EpiTraits<EPI>::kLoads) prefetch_tmap(&tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -282,6 +439,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&tmem_full_bar[b], 1);
         mbar_init(&tmem_empty_bar[b], EPI_WARPS);    // one arrival per epilogue warp
       }
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&epi_bar[w], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -364,61 +522,91 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int WPQ = EPI_WARPS / 4;         // warps per TMEM lane quarter
     const int q = warp & 3;                    // lane quarter this warp may access
     const int sub = (warp - 2) >> 2;           // which warp of that quarter: chunks c = sub, sub + WPQ, ...
-    const uint32_t stage = smem_u32(epi_stage) + (warp - 2) * (16 * STAGE_LD * 4);
+    uint8_t* buf_ptr = epi_stage + (warp - 2) * EPI_BUF_BYTES;
+    const uint32_t buf = smem_u32(buf_ptr);
+    uint64_t* ebar = &epi_bar[warp - 2];
+    uint32_t eph = 0;
+    constexpr int CW = EPI == FC_EPI_PATCH ? 32 : EpiTraits<EPI>::kCW;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % tiles_mn;
       const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
-      const int buf = it & 1;
-      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      const int buf_i = it & 1;
+      mbar_wait(&tmem_full_bar[buf_i], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
-      // chunks this warp owns: c = sub, sub+WPQ, ... ; the last one it will actually read (col0 < N)
+      const uint32_t taddr = tmem_base + buf_i * TMEM_BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      const int row0 = m0 + q * 32;
+      // chunks this warp owns: c = sub, sub+WPQ, ... ; the last one it will actually read (col0 < N, rows < M)
       int last_c = -1;
-      for (int c = sub; c < BN / 32; c += WPQ)
-        if (n0 + c * 32 < p.N) last_c = c;
+      if (row0 < p.M)
+        for (int c = sub; c < BN / CW; c += WPQ)
+          if (n0 + c * CW < p.N) last_c = c;
       if (last_c < 0 || (p.debug & 1)) {       // nothing to read in this tile (or main-loop-only timing)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
         continue;
       }
 #pragma unroll 1
       for (int c = sub; c <= last_c; c += WPQ) {
-        const int col0 = n0 + c * 32;
-        // global operands of this chunk first: their latency overlaps the TMEM load and the transposes
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int bcol = col0 + (lane & 7) * 4;
-        if (p.bias != nullptr && bcol < p.N) bias = __ldg(reinterpret_cast<const float4*>(p.bias + bcol));
-        EpiPre<EPI> pre;
-        epilogue_prefetch<EPI>(p, pre, m0 + q * 32, col0, lane);
-        float acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        if (c == last_c) {                     // last TMEM read of this tile by this warp: hand the buffer back
-          tc_fence_before();
+        const int col0 = n0 + c * CW;
+        if constexpr (EPI == FC_EPI_PATCH) {
+          // legacy path (row remap b*P+t -> b*(P+1)+1+t cannot be expressed as one TMA box): transpose via smem
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int bcol = col0 + (lane & 7) * 4;
+          if (p.bias != nullptr && bcol < p.N) bias = __ldg(reinterpret_cast<const float4*>(p.bias + bcol));
+          EpiPre<EPI> pre;
+          float acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          if (c == last_c) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
+          }
+          if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_v4(buf + (lane * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        // transpose through smem, 16 rows per pass: thread = row  ->  8 lanes per row, 4 columns each
-        if (lane < 16) {
+          epilogue_block<EPI, 0>(p, buf, row0, col0, lane, bias, pre);
+          __syncwarp();
+          if (lane >= 16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts_v4(stage + (lane * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              sts_v4(buf + ((lane - 16) * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+          __syncwarp();
+          epilogue_block<EPI, 1>(p, buf, row0, col0, lane, bias, pre);
+          __syncwarp();
+        } else {
+          if constexpr (EpiTraits<EPI>::kLoads) {     // fused operand tile (residual / saved gelu') -> staging buffer
+            if (lane == 0) {
+              tma_store_wait_read();           // the previous store out of this buffer has drained
+              mbar_arrive_expect_tx(ebar, EPI_BUF_BYTES);
+              tma_load_2d(buf_ptr, &tmR, ebar, col0, row0);
+            }
+          }
+          float acc[CW];
+          {
+            float(&lo)[32] = *reinterpret_cast<float(*)[32]>(&acc[0]);
+            tmem_ld_32x32(taddr + c * CW, lo);
+            if constexpr (CW == 64) {
+              float(&hi)[32] = *reinterpret_cast<float(*)[32]>(&acc[32]);
+              tmem_ld_32x32(taddr + c * CW + 32, hi);
+            }
+          }
+          tmem_ld_wait();
+          if (c == last_c) {                   // last TMEM read of this tile by this warp: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
+          }
+          epilogue_tma_chunk<EPI>(p, &tmO, &tmO2, buf_ptr, buf, ebar, eph, acc, row0, col0, lane);
         }
-        __syncwarp();
-        epilogue_block<EPI, 0>(p, stage, m0 + q * 32, col0, lane, bias, pre);
-        __syncwarp();
-        if (lane >= 16) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts_v4(stage + ((lane - 16) * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2],
-                   acc[4 * j + 3]);
-        }
-        __syncwarp();
-        epilogue_block<EPI, 1>(p, stage, m0 + q * 32, col0, lane, bias, pre);
-        __syncwarp();
       }
     }
+    if (lane == 0) tma_store_wait_all();       // all bulk stores of this warp are globally complete before exit
   }
   __syncthreads();
   if (warp == 1) {
@@ -445,16 +633,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major matrix [rows, cols] with leading dimension ld; box = {box_cols, box_rows}
+// row-major matrix [rows, cols] (bf16, or fp32 when f32 != 0) with leading dimension ld; box = {box_cols, box_rows}
 int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
-              int box_rows) {
+              int box_rows, int f32 = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
@@ -467,8 +655,11 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 int g_prof_on = 0;
 
+struct EpiMaps { CUtensorMap o, o2, r; };
+
 template <int BN, int A_MN, int B_MN, int EPI>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int device,
+           cudaStream_t st) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   FC_SMEM_OPT_IN(kern, Cfg<BN>::SMEM_BYTES);
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -481,7 +672,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     cudaEventCreate(&rec.b);
     cudaEventRecord(rec.a, st);
   }
-  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
   if (prof) {
     cudaEventRecord(rec.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -497,10 +688,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 //   dW       A,B MN-major       : ATOMIC_F32, F32
 //   (A MN, B K)                 : F32 (parity tests)
 template <int BN>
-int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int a_mn, int b_mn, int device,
-              cudaStream_t st) {
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int a_mn, int b_mn,
+              int device, cudaStream_t st) {
 #define FC_CASE(AM, BMJ, E) \
-  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E>(ta, tb, p, device, st)
+  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E>(ta, tb, em, p, device, st)
   FC_CASE(0, 0, FC_EPI_BF16); FC_CASE(0, 0, FC_EPI_GELU); FC_CASE(0, 0, FC_EPI_RESID); FC_CASE(0, 0, FC_EPI_F32);
   FC_CASE(0, 0, FC_EPI_PATCH);
   FC_CASE(0, 1, FC_EPI_BF16); FC_CASE(0, 1, FC_EPI_MULAUX); FC_CASE(0, 1, FC_EPI_F32);
@@ -612,8 +803,30 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   if (rc) return rc;
   rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, bn);
   if (rc) return rc;
+  // epilogue tiles: 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), stored / reduced / loaded by TMA
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (epi != FC_EPI_PATCH) {
+    const int out16 = (epi == FC_EPI_BF16 || epi == FC_EPI_GELU || epi == FC_EPI_MULAUX);
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out16 ? 2 : 4)) % 16 == 0,
+               "fc_gemm_bf16: output must be 16-byte aligned with a 16-byte multiple row pitch");
+    rc = make_tmap(&em.o, out, M, N, ldo, out16 ? 64 : 32, 32, !out16);
+    if (rc) return rc;
+    if (epi == FC_EPI_GELU) {
+      rc = make_tmap(&em.o2, out2, M, N, ldo, 64, 32, 0);
+      if (rc) return rc;
+    }
+    if (epi == FC_EPI_RESID) {
+      rc = make_tmap(&em.r, resid, M, N, ldo, 32, 32, 1);
+      if (rc) return rc;
+    }
+    if (epi == FC_EPI_MULAUX) {
+      rc = make_tmap(&em.r, aux, M, N, ldo, 64, 32, 0);
+      if (rc) return rc;
+    }
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_bn<256>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
-  if (bn == 192) return launch_bn<192>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
-  return launch_bn<128>(ta, tb, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  if (bn == 256) return launch_bn<256>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  if (bn == 192) return launch_bn<192>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  return launch_bn<128>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
 }
