@@ -37,13 +37,14 @@ constexpr int EPI_WARPS = 16;              // four warps per TMEM lane quarter, 
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 constexpr int STAGE_LD = 36;               // floats per row of the legacy transpose buffer (PATCH epilogue only)
 constexpr int EPI_BUF_BYTES = 32 * 128;    // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store/load tile)
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;
+constexpr int EPI_BIAS_BYTES = 64 * 4;      // per epilogue warp: the bias of the chunk's (up to) 64 columns
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * (EPI_BUF_BYTES + EPI_BIAS_BYTES);
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
 template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);   // what fits beside the epilogue staging
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 3 : 4);   // what fits beside the epilogue staging
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
@@ -299,18 +300,18 @@ __device__ __forceinline__ void stage_acquire(int lane) {
 // One 32-row x kCW-column chunk of the accumulator (acc[] = this lane's row) -> global, fused op EPI.
 template <int EPI>
 __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmO2,
-                                                   uint8_t* buf_ptr, uint32_t buf, uint64_t* ebar, uint32_t& eph,
-                                                   float (&acc)[EpiTraits<EPI>::kCW], int row0, int col0, int lane) {
+                                                   uint8_t* buf_ptr, uint32_t buf, uint32_t bias_smem, uint64_t* ebar,
+                                                   uint32_t& eph, float (&acc)[EpiTraits<EPI>::kCW], int row0, int col0,
+                                                   int lane) {
   constexpr int CW = EpiTraits<EPI>::kCW;
   const int t = lane;
-  // bias: the same 4 columns for every lane -> uniform (broadcast) loads
+  // bias of the chunk's columns was staged in shared memory by this warp (one coalesced load, issued before the
+  // TMEM read): every lane needs all of it -> broadcast LDS.128
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) {
-      if (col0 + 4 * j < p.N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
-        acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
-      }
+      const float4 b = lds_v4(bias_smem + 16 * j);
+      acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
     }
   }
   if constexpr (EPI == FC_EPI_BF16) {
@@ -524,6 +525,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = (warp - 2) >> 2;           // which warp of that quarter: chunks c = sub, sub + WPQ, ...
     uint8_t* buf_ptr = epi_stage + (warp - 2) * EPI_BUF_BYTES;
     const uint32_t buf = smem_u32(buf_ptr);
+    const uint32_t bias_smem = smem_u32(epi_stage) + EPI_WARPS * EPI_BUF_BYTES + (warp - 2) * EPI_BIAS_BYTES;
     uint64_t* ebar = &epi_bar[warp - 2];
     uint32_t eph = 0;
     constexpr int CW = EPI == FC_EPI_PATCH ? 32 : EpiTraits<EPI>::kCW;
@@ -587,6 +589,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(buf_ptr, &tmR, ebar, col0, row0);
             }
           }
+          // the chunk's bias: lane l fetches columns col0 + 2l, 2l+1 now (latency overlaps the TMEM read) ...
+          float2 b2 = make_float2(0.f, 0.f);
+          if (p.bias != nullptr && 2 * lane < CW && col0 + 2 * lane < p.N)
+            b2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + 2 * lane));
           float acc[CW];
           {
             float(&lo)[32] = *reinterpret_cast<float(*)[32]>(&acc[0]);
@@ -602,7 +608,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
           }
-          epilogue_tma_chunk<EPI>(p, &tmO, &tmO2, buf_ptr, buf, ebar, eph, acc, row0, col0, lane);
+          if (p.bias != nullptr) {             // ... and shares it with the other lanes through shared memory
+            if (2 * lane < CW)
+              asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_smem + 8 * lane), "f"(b2.x), "f"(b2.y) : "memory");
+            __syncwarp();
+          }
+          epilogue_tma_chunk<EPI>(p, &tmO, &tmO2, buf_ptr, buf, bias_smem, ebar, eph, acc, row0, col0, lane);
         }
       }
     }
