@@ -7,9 +7,9 @@
 // multiple of 16 are masked.  One CTA per (sample, head); the whole head (N <= 256 tokens) lives in
 // shared memory, so the [B,H,N,N] probability tensor is never materialised in HBM.
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix from
-// padded shared memory.  The tcgen05 version (S and O accumulators in TMEM) is the next step; this path
-// carries ~8% (img) / ~3% (txt) of the model FLOPs.
+// This file holds the BACKWARD: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix from
+// swizzled shared memory (round-1 implementation; its tcgen05 rewrite is the next step).  The forward is the
+// tcgen05/TMEM kernel in attention_tc.cu.
 #include "common.cuh"
 #include "../../include/fedcola_b200.h"
 
@@ -104,91 +104,6 @@ __device__ __forceinline__ void tile_colsum(float* dst, uint32_t w0, uint32_t w1
   if (lane < 4) {
     atomicAdd(dst, x);
     atomicAdd(dst + 1, y);
-  }
-}
-
-// ---- forward ------------------------------------------------------------------------------------
-template <int NPAD>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                                                       int N, int H, float scale) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* Ks = Qs + NPAD * LDS;
-  __nv_bfloat16* Vs = Ks + NPAD * LDS;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int d = H * HD;
-  const long long rs = 3LL * d;
-  const __nv_bfloat16* base = qkv + (size_t)b * N * rs + h * HD;
-  stage_rows(Qs, base, rs, N, NPAD);
-  stage_rows(Ks, base + d, rs, N, NPAD);
-  stage_rows(Vs, base + 2 * d, rs, N, NPAD);
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  constexpr int NT = NPAD / 16;
-  for (int mt = warp; mt < NT; mt += 4) {
-    uint32_t qa[4][4];
-    load_a_frags(qa, Qs, mt * 16, lane);
-    float s[NT][2][4];
-#pragma unroll
-    for (int ct = 0; ct < NT; ++ct) mma_rowsT(s[ct], qa, Ks, ct * 16, lane);
-    // scale, mask padding columns, row max (rows g and g+8)
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int ct = 0; ct < NT; ++ct)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = ct * 16 + j * 8 + 2 * t + (i & 1);
-          float v = s[ct][j][i] * scale;
-          if (col >= N) v = -INFINITY;
-          s[ct][j][i] = v;
-          if (i < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-        }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int ct = 0; ct < NT; ++ct)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float e = __expf(s[ct][j][i] - (i < 2 ? mx0 : mx1));
-          s[ct][j][i] = e;
-          if (i < 2) sum0 += e; else sum1 += e;
-        }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-    const int row0 = mt * 16 + g, row1 = row0 + 8;
-    if (lse != nullptr && t == 0) {
-      if (row0 < N) lse[((size_t)b * H + h) * N + row0] = mx0 + __logf(sum0);
-      if (row1 < N) lse[((size_t)b * H + h) * N + row1] = mx1 + __logf(sum1);
-    }
-    // O = softmax(S) (cast to bf16, as `.type_as(x)` does) * V
-    float o[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
-#pragma unroll
-    for (int ct = 0; ct < NT; ++ct) {
-      uint32_t p[4];
-      p[0] = pack2(s[ct][0][0] * inv0, s[ct][0][1] * inv0);
-      p[1] = pack2(s[ct][0][2] * inv1, s[ct][0][3] * inv1);
-      p[2] = pack2(s[ct][1][0] * inv0, s[ct][1][1] * inv0);
-      p[3] = pack2(s[ct][1][2] * inv1, s[ct][1][3] * inv1);
-      mma_rows(o, p, Vs, ct * 16, lane);
-    }
-    __nv_bfloat16* ob = out + (size_t)b * N * d + h * HD;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (row0 < N) *reinterpret_cast<uint32_t*>(ob + (size_t)row0 * d + n * 8 + 2 * t) = pack2(o[n][0], o[n][1]);
-      if (row1 < N) *reinterpret_cast<uint32_t*>(ob + (size_t)row1 * d + n * 8 + 2 * t) = pack2(o[n][2], o[n][3]);
-    }
   }
 }
 
@@ -350,15 +265,6 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat1
 }
 
 template <int NPAD>
-int launch_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int N, int H, float scale,
-               cudaStream_t st) {
-  const int smem = 3 * NPAD * LDS * 2;
-  FC_SMEM_OPT_IN(attn_fwd_kernel<NPAD>, smem);
-  attn_fwd_kernel<NPAD><<<B * H, 128, smem, st>>>(qkv, out, lse, N, H, scale);
-  FC_LAUNCH_CHECK();
-  return FC_OK;
-}
-template <int NPAD>
 int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse,
                __nv_bfloat16* dqkv, float* dbias, int B, int N, int H, float scale, cudaStream_t st) {
   const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4 + 3 * HD * 4;
@@ -371,21 +277,6 @@ int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bflo
 }
 
 }  // namespace
-
-extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim,
-                                int device, void* stream) {
-  FC_REQUIRE(head_dim == HD, "fc_attention_fwd: head_dim must be 64 (got %d)", head_dim);
-  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0, "fc_attention_fwd: unsupported shape B=%d N=%d H=%d", B, N, H);
-  FcDeviceGuard guard(device);
-  const float scale = 0.125f;   // 64^-0.5
-  auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  auto o = reinterpret_cast<__nv_bfloat16*>(out);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N <= 48) return launch_fwd<48>(q, o, lse, B, N, H, scale, st);
-  if (N <= 64) return launch_fwd<64>(q, o, lse, B, N, H, scale, st);
-  if (N <= 208) return launch_fwd<208>(q, o, lse, B, N, H, scale, st);
-  return launch_fwd<256>(q, o, lse, B, N, H, scale, st);
-}
 
 extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                                 float* dbias, int B, int N, int H, int head_dim, int device, void* stream) {

@@ -1,0 +1,423 @@
+// tcgen05 fused short-sequence attention, forward (head_dim 64, N <= 256 tokens).
+//
+// Replaces Attention.forward between the qkv and proj Linears (/root/reference/src/models/mome.py:153-165):
+// q*scale, fp32 QK^T, fp32 softmax, cast, P·V, head merge.  Persistent CTAs (one per SM, 16 warps) walk the
+// (sample, head) items:
+//   TMA (3-D tensor maps over qkv [B, N, 3*H*64], 128-byte swizzle) stages Q, K, V of an item in shared memory —
+//   token rows >= N are zero-filled by the TMA unit; the next item is prefetched into a second buffer;
+//   S = Q K^T   : tcgen05.mma  M=128 queries, N=NK (keys padded to 16), K=64      -> TMEM (double-buffered, col 0/256)
+//   softmax     : TMEM lane = query row; the 4 warps of a lane quarter split the key columns 64 each, keep their
+//                 scores in registers (one tcgen05.ld pass), exchange row max / row sum through smem, and write
+//                 the normalised bf16 P tile (swizzled, K-major) for the second MMA;
+//   O = P V     : tcgen05.mma  M=128, N=64, K=NK (A = P K-major, B = V MN-major)  -> overlays the consumed S
+//   epilogue    : O -> bf16 -> 32-byte row segments straight to global (rows >= N skipped);
+//                 LSE = max + log(sum) for the backward.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "../../include/fedcola_b200.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+using namespace sm100;
+
+constexpr int HD = 64;
+constexpr int TILE = 128 * 128;            // bytes of one 128-row x 128-byte swizzled tile (16 KB)
+#ifdef FC_ATTN_PROF
+__device__ long long g_attn_prof[16 * 12];
+#define PROF(slot) do { if (threadIdx.x == 0 && T < 16) prof_s[T * 12 + (slot)] = clock64(); } while (0)
+#else
+#define PROF(slot) do { } while (0)
+#endif
+#ifdef FC_ATTN_PROF
+constexpr int kMaxDynSmem = 232448 - 2048;
+#else
+constexpr int kMaxDynSmem = 232448;
+#endif
+constexpr int kSoftmaxWarps = 16;          // warp&3 = TMEM lane quarter (query rows), warp>>2 = 64-column group
+constexpr int kFwdThreads = (kSoftmaxWarps + 1) * 32;   // + one control warp (TMA producer / MMA issuer)
+
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_bf16(uint32_t addr, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+}
+__device__ __forceinline__ float ld_shared_bf16(uint32_t addr) {
+  uint16_t h;
+  asm volatile("ld.shared.b16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// MN-major B operand made of ONE 64-wide block (V: rows = keys = K index, 128-byte rows of 64 head-dim values)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_desc(addr, 8192, 1024); }
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }
+
+struct FwdMaps {
+  CUtensorMap qkv_a, qkv_b;                  // box rows RA (first 128-token tile) / RB (remainder tile)
+};
+
+// Persistent: CTA c handles (sample, head) items c, c+grid, ...  Warp 16 is the control warp: its lane 0 prefetches
+// the next items' Q/K/V by TMA (nbuf smem buffers) and issues every tcgen05.mma; warps 0-15 do the softmax and the
+// output.  S accumulators are double-buffered in TMEM (columns 0 / 256) and O overlays its own consumed S, so
+// QK^T of tile T+1 and P·V of tile T run under the softmax warps' work on the neighbouring tiles.
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                   int n_items, int N, int H, int nbuf, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
+#ifdef FC_ATTN_PROF
+  __shared__ long long prof_s[16 * 12];
+#endif
+  if (smem_u32(smem) & 1023) __trap();
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;                     // keys padded to the UMMA N granularity; rows >= N are TMA zero fill
+  const int q_tiles = RB ? 2 : 1;
+  const int op_bytes = NK * 128;              // one operand (Q, K or V) of one item
+  const int buf_bytes = 3 * op_bytes;
+  const int n_pblk = (NK + 63) >> 6;
+  uint8_t* p_base = smem + nbuf * buf_bytes;
+  // reduction scratch, double-buffered by tile parity: row-sum partials float [2][4][128], then row-max partials
+  // bf16 [2][4][128] (softmax is shift-invariant: a rounded max only has to be the SAME for the whole row)
+  uint8_t* red_base = p_base + n_pblk * TILE;
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(red_base + 6144);    // [4] item operands landed
+  uint64_t* s_full = tma_bar + 4;                                      // [2] S buffer written by the tensor core
+  uint64_t* o_full = s_full + 2;                                       //     O written (and P, V no longer read)
+  uint64_t* p_full = o_full + 1;                                       //     P tile written by the 16 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+  const uint32_t sP = smem_u32(p_base);
+  const int d = H * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&tma_bar[i], 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(o_full, 1);
+    mbar_init(p_full, kSoftmaxWarps);
+    fence_barrier_init();
+  }
+  if (warp == kSoftmaxWarps) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: NK <= 208: S0 [0,208) S1 [208,416) O [416,480); larger NK: one S buffer [0,256), O [256,320)
+  const int depth = NK <= 208 ? 2 : 1;
+  const uint32_t s_stride = 208, o_col = NK <= 208 ? 416 : 256;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+
+  if (warp == kSoftmaxWarps) {
+    // ================= control warp: TMA producer + MMA issuer (one lane) =================
+    if (lane == 0 && n_my > 0) {
+      prefetch_tmap(&maps.qkv_a);
+      prefetch_tmap(&maps.qkv_b);
+      const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      auto buf_addr = [&](int k) { return smem_u32(smem) + (k % nbuf) * buf_bytes; };
+      auto issue_load = [&](int k) {
+        const int item = first + k * stride;
+        const int b = item / H, h = item % H;
+        uint8_t* base = smem + (k % nbuf) * buf_bytes;
+        uint64_t* bar = &tma_bar[k % nbuf];
+        mbar_arrive_expect_tx(bar, buf_bytes);
+        for (int op = 0; op < 3; ++op) {      // Q, K, V column blocks of this head
+          tma_load_3d(base + op * op_bytes, &maps.qkv_a, bar, op * d + h * HD, 0, b);
+          if (RB) tma_load_3d(base + op * op_bytes + RA * 128, &maps.qkv_b, bar, op * d + h * HD, 128, b);
+        }
+      };
+      auto issue_s = [&](int k, int qt, int sbuf) {   // S[sbuf] = Q_tile K^T
+        if (qt == 0) mbar_wait(&tma_bar[k % nbuf], (k / nbuf) & 1);
+        tc_fence_after();
+        const uint32_t q = buf_addr(k) + qt * TILE, kk = buf_addr(k) + op_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem + sbuf * s_stride, desc_k(q + j * 32), desc_k(kk + j * 32), idesc_s, j > 0);
+        umma_commit(&s_full[sbuf]);
+      };
+      // Issue order is a small state machine: loads run up to nbuf items ahead (a buffer is reusable once the last
+      // P·V of its item completed), QK^T runs up to `depth` tiles ahead of the softmax (an S buffer is reusable
+      // once the softmax warps consumed it, i.e. p_full of that tile), P·V follows p_full.
+      const int total = n_my * q_tiles;
+      int next_load = 0, next_s = 0, done_items = 0;
+      auto pump = [&](int T) {
+        while (next_load < n_my && next_load < done_items + nbuf) issue_load(next_load++);
+        while (next_s < total && next_s < T + depth && next_s / q_tiles < next_load) {
+          issue_s(next_s / q_tiles, next_s % q_tiles, next_s % depth);
+          ++next_s;
+        }
+      };
+      pump(0);
+      for (int T = 0; T < total; ++T) {
+        const int k = T / q_tiles;
+        while (!mbar_try_wait(p_full, T & 1)) __nanosleep(100);   // P_T in smem, S_T consumed, O_{T-1} read
+        tc_fence_after();
+        const uint32_t vv = buf_addr(k) + 2 * op_bytes;
+        const int ksteps = NK >> 4;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(tmem + o_col, desc_k(sP + (ks >> 2) * TILE + (ks & 3) * 32), desc_mn(vv + ks * 2048), idesc_o,
+                    ks > 0);
+        umma_commit(o_full);
+        pump(T + 1);
+        if ((T + 1) % q_tiles == 0) {
+          mbar_wait(o_full, T & 1);           // every MMA reading buffer k % nbuf has completed
+          ++done_items;
+          pump(T + 1);
+        }
+      }
+    }
+  } else {
+    // ================= softmax warps =================
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int row = quarter * 32 + lane;      // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int c0 = grp * 64;
+    const int nc = min(max(NK - c0, 0), 64);  // columns of this warp (multiple of 16)
+    const int valid = min(nc, N - c0);        // ... of which real keys
+    const uint32_t red_sum = smem_u32(red_base) + (grp * 128 + row) * 4, red_sum_rd = smem_u32(red_base) + row * 4;
+    const uint32_t red_max = smem_u32(red_base) + 4096 + (grp * 128 + row) * 2;
+    const uint32_t red_max_rd = smem_u32(red_base) + 4096 + row * 2;
+    // swizzled address of 16-byte chunk j of this thread's P row = p_swz ^ (j << 4)   (tile base is 1024-aligned)
+    const uint32_t p_swz = (sP + grp * TILE + row * 128) | ((row & 7) << 4);
+    // one 32-wide (or trailing 16-wide) slab of this thread's score row; returns the number of columns loaded
+    auto load_slab = [&](uint32_t tS, int half, float (&v)[32]) -> int {
+      const int n = min(nc - 32 * half, 32);
+      if (n == 32) tmem_ld_32x32(tS + lane_off + c0 + 32 * half, v);
+      else if (n == 16) tmem_ld_32x16(tS + lane_off + c0 + 32 * half, *reinterpret_cast<float(*)[16]>(&v[0]));
+      tmem_ld_wait();
+      return n;
+    };
+    // O of a finished tile (columns [16*grp, +16) of this thread's row), scaled by that tile's 1/rowsum.  Loaded
+    // before this tile's P is published (the next P·V overwrites O), stored after it (a proxy fence behind
+    // outstanding global stores would wait for them).
+    auto load_o = [&](int T, float inv, uint32_t (&o)[8]) {
+      mbar_wait(o_full, T & 1);
+      tc_fence_after();
+      float f[16];
+      tmem_ld_32x16(tmem + o_col + lane_off + grp * 16, f);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack2(f[2 * i] * inv, f[2 * i + 1] * inv);
+    };
+    auto store_o = [&](const uint32_t (&o)[8], int bh_row0, int h, int qt) {
+      const int qrow = qt * 128 + row;
+      if (qrow < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(bh_row0) + qrow) * d + h * HD + grp * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    };
+    // keys >= N of a slab (columns at or beyond `nvalid`) -> -inf; only the slab holding the padding boundary
+    auto mask_slab = [&](float (&v)[32], int nvalid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
+    };
+    const float sc = scale_log2e;
+    // row sums of the previous tile -> 1/sum for its O rows, LSE for the backward
+    auto finish_sums = [&](int T, float mb, int bh, int qt) -> float {
+      const uint32_t rd = red_sum_rd + (T & 1) * 2048;
+      const float sum = (ld_shared_f32(rd) + ld_shared_f32(rd + 512)) + (ld_shared_f32(rd + 1024) + ld_shared_f32(rd + 1536));
+      const int qrow = qt * 128 + row;
+      if (grp == 0 && lse_out != nullptr && qrow < N)
+        lse_out[static_cast<size_t>(bh) * N + qrow] = 0.69314718056f * (mb + lg2(sum));
+      return rcp(sum);
+    };
+    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0;
+    float prev_mb = 0.f;
+    const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;   // item / H == (item * magic) >> 32 for item < 2^16
+    for (int k = 0, item = first; k < n_my; ++k, item += stride) {
+      const int b = static_cast<int>((static_cast<unsigned long long>(item) * h_magic) >> 32), h = item - b * H;
+      for (int qt = 0; qt < q_tiles; ++qt, ++T) {
+        const int sb = depth == 2 ? (T & 1) : 0;
+        const uint32_t tS = tmem + sb * s_stride;
+        const uint32_t par = (T & 1) * 1024;  // reduction scratch is double-buffered by tile parity: one barrier/tile
+        PROF(0);
+        mbar_wait(&s_full[sb], (depth == 2 ? (T >> 1) : T) & 1);
+        tc_fence_after();
+        PROF(1);
+        // ---- pass 1: row max over this warp's columns (keys >= N masked) ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (32 * half < nc) {                // warp-uniform
+            float v[32];
+            const int n = load_slab(tS, half, v);
+            if (32 * half + n > valid) mask_slab(v, valid - 32 * half);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (i < n) {
+                m0 = fmaxf(m0, v[i]);
+                m1 = fmaxf(m1, v[i + 1]);
+              }
+            }
+          }
+        }
+        st_shared_bf16(red_max + par, fmaxf(m0, m1));
+        softmax_warps_sync();                 // also: every warp has published the previous tile's row sums
+        PROF(3);
+        const float mx = fmaxf(fmaxf(ld_shared_bf16(red_max_rd + par), ld_shared_bf16(red_max_rd + par + 256)),
+                               fmaxf(ld_shared_bf16(red_max_rd + par + 512), ld_shared_bf16(red_max_rd + par + 768)));
+        const float mb = mx * sc, nmb = -mb;
+        // the previous tile's P·V ran under the work above: fetch its O now (this also frees the P tile)
+        uint32_t o[8];
+        if (T > 0) load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
+        PROF(4);
+        // ---- pass 2: p = exp2(s*c - max*c) -> bf16 -> swizzled K-major P tile (column block = grp); row sum ----
+        // P is left un-normalised (0 < p <= 1); the row of O is scaled by 1/sum in its epilogue.
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (32 * half < nc) {
+            float v[32];
+            const int n = load_slab(tS, half, v);
+            if (32 * half + n > valid) mask_slab(v, valid - 32 * half);   // exp2(-inf) = 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < n) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = 8 * j + 2 * e;
+                  const float p0 = ex2(fmaf(v[i], sc, nmb));
+                  const float p1 = ex2(fmaf(v[i + 1], sc, nmb));
+                  s0 += p0;
+                  s1 += p1;
+                  pk[e] = pack2(p0, p1);
+                }
+                sts_u4(p_swz ^ ((4 * half + j) << 4), pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+        st_shared_f32(red_sum + 2 * par, s0 + s1);
+        fence_proxy_async();                  // P (generic-proxy writes) -> visible to the tensor core's smem reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        PROF(5);
+        if (T > 0) store_o(o, prev_row0, prev_h, prev_qt);
+        prev_mb = mb;
+        prev_row0 = b * N;
+        prev_bh = item;
+        prev_h = h;
+        prev_qt = qt;
+        PROF(6);
+      }
+    }
+    if (T > 0) {
+      softmax_warps_sync();                   // last tile's row sums
+      uint32_t o[8];
+      load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
+      store_o(o, prev_row0, prev_h, prev_qt);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+#ifdef FC_ATTN_PROF
+  if (blockIdx.x == 0 && threadIdx.x < 16 * 12) g_attn_prof[threadIdx.x] = prof_s[threadIdx.x];
+#endif
+  if (warp == kSoftmaxWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+// bf16 [B, N, width] row-major; box = 64 columns x `rows` token rows x 1 sample, 128-byte swizzle
+int make_tmap3(CUtensorMap* m, const void* ptr, int B, int N, int width, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)width * 2, (cuuint64_t)N * width * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed (%d)", (int)r);
+  return FC_OK;
+}
+
+}  // namespace
+
+extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim,
+                                int device, void* stream) {
+  FC_REQUIRE(head_dim == HD, "fc_attention_fwd: head_dim must be 64 (got %d)", head_dim);
+  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
+             "fc_attention_fwd: unsupported shape B=%d N=%d H=%d", B, N, H);
+  FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "fc_attention_fwd: qkv/out must be 16-byte aligned");
+  FcDeviceGuard guard(device);
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;
+  FwdMaps maps;
+  int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
+  if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
+  if (rc) return rc;
+  const int buf_bytes = 3 * NK * 128, p_bytes = ((NK + 63) / 64) * TILE, aux = 6144 + 128;
+  int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
+  while (nbuf > 1 && nbuf * buf_bytes + p_bytes + aux > kMaxDynSmem) --nbuf;
+  const int smem = nbuf * buf_bytes + p_bytes + aux;
+  FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
+  const int items = B * H;
+  const int sms = fc_num_sms(device);
+  const int waves = (items + sms - 1) / sms;
+  const int grid = (items + waves - 1) / waves;                  // balanced persistent grid (<= #SMs)
+  const float scale_log2e = 0.125f * 1.4426950408889634f;        // 64^-0.5 * log2(e)
+  attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      maps, static_cast<__nv_bfloat16*>(out), lse, items, N, H, nbuf, scale_log2e);
+  FC_LAUNCH_CHECK();
+  return FC_OK;
+}

@@ -26,13 +26,22 @@ def _attn_ref(qkv, B, N, H):
     return (attn_b @ v).transpose(1, 2).reshape(B, N, H * 64), attn
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 6), (2, 40, 1), (1, 16, 2), (2, 200, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 6), (2, 40, 1), (1, 16, 2), (2, 200, 2), (2, 256, 2),
+                                   (3, 129, 1), (2, 128, 3), (5, 1, 2), (4, 7, 1)])
 def test_attention_forward(B, N, H, cuda):
     torch.manual_seed(0)
     qkv = (torch.randn(B, N, 3, H, 64, device=cuda) * 1.5).to(torch.bfloat16)
     out, lse = ops.attention_fwd(qkv, B, N, H)
     ref, _ = _attn_ref(qkv, B, N, H)
-    _close(out, ref, 2 ** -7, 2e-3, "out")
+    # The kernel rounds the un-normalised probabilities exp(s - max) to bf16 and divides the fp32 row of P·V by the
+    # fp32 row sum; the reference pipeline in bf16 would round the normalised ones.  Both are a 2^-9 relative
+    # rounding of every term of a convex combination of V rows: |error| <= ~2^-8 * max|V| + output rounding.
+    vmax = qkv.float().view(B, N, 3, H, 64)[:, :, 2].abs().max().item()
+    _close(out, ref, 2 ** -7, 2 ** -8 * vmax, "out")
+    x = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    exact = (((x[0] * 0.125) @ x[1].transpose(-2, -1)).softmax(-1) @ x[2]).transpose(1, 2).reshape(B, N, H * 64)
+    rel = (out.float() - exact).norm() / exact.norm()
+    assert rel < 4e-3, rel                            # aggregate error vs the fp32 op: bf16 output rounding level
     q, k, _ = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
     ref_lse = torch.logsumexp((q * 0.125) @ k.transpose(-2, -1), dim=-1)
     _close(lse, ref_lse, 1e-4, 1e-3, "lse")
