@@ -108,17 +108,14 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
   const int q_tiles = RB ? 2 : 1;
   const int op_bytes = NK * 128;              // one operand (Q, K or V) of one item
   const int buf_bytes = 3 * op_bytes;
-  const int n_pblk = (NK + 63) >> 6;
-  uint8_t* p_base = smem + nbuf * buf_bytes;
   // reduction scratch, double-buffered by tile parity: row-sum partials float [2][4][128], then row-max partials
   // bf16 [2][4][128] (softmax is shift-invariant: a rounded max only has to be the SAME for the whole row)
-  uint8_t* red_base = p_base + n_pblk * TILE;
+  uint8_t* red_base = smem + nbuf * buf_bytes;
   uint64_t* tma_bar = reinterpret_cast<uint64_t*>(red_base + 6144);    // [4] item operands landed
   uint64_t* s_full = tma_bar + 4;                                      // [2] S buffer written by the tensor core
   uint64_t* o_full = s_full + 2;                                       //     O written (and P, V no longer read)
   uint64_t* p_full = o_full + 1;                                       //     P tile written by the 16 softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
-  const uint32_t sP = smem_u32(p_base);
   const int d = H * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -191,9 +188,12 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
         tc_fence_after();
         const uint32_t vv = buf_addr(k) + 2 * op_bytes;
         const int ksteps = NK >> 4;
+        // P (bf16 pairs) sits in the S buffer: the 16 keys of k-step ks occupy 8 columns at 64*(ks/4) + 16*(ks%4) —
+        // each softmax warp packed its 32-score slabs in place (slab at +32*half, packed into its first 16 columns)
+        const uint32_t tP = tmem + (depth == 2 ? (T & 1) : 0) * s_stride;
         for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16(tmem + o_col, desc_k(sP + (ks >> 2) * TILE + (ks & 3) * 32), desc_mn(vv + ks * 2048), idesc_o,
-                    ks > 0);
+          umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), desc_mn(vv + ks * 2048),
+                       idesc_o, ks > 0);
         umma_commit(o_full);
         pump(T + 1);
         if ((T + 1) % q_tiles == 0) {
@@ -214,8 +214,6 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
     const uint32_t red_sum = smem_u32(red_base) + (grp * 128 + row) * 4, red_sum_rd = smem_u32(red_base) + row * 4;
     const uint32_t red_max = smem_u32(red_base) + 4096 + (grp * 128 + row) * 2;
     const uint32_t red_max_rd = smem_u32(red_base) + 4096 + row * 2;
-    // swizzled address of 16-byte chunk j of this thread's P row = p_swz ^ (j << 4)   (tile base is 1024-aligned)
-    const uint32_t p_swz = (sP + grp * TILE + row * 128) | ((row & 7) << 4);
     // one 32-wide (or trailing 16-wide) slab of this thread's score row; returns the number of columns loaded
     auto load_slab = [&](uint32_t tS, int half, float (&v)[32]) -> int {
       const int n = min(nc - 32 * half, 32);
@@ -321,13 +319,14 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
                   s1 += p1;
                   pk[e] = pack2(p0, p1);
                 }
-                sts_u4(p_swz ^ ((4 * half + j) << 4), pk[0], pk[1], pk[2], pk[3]);
+                // 8 keys -> 4 packed columns, written over this thread's own (already consumed) scores
+                tmem_st_32x4(tS + lane_off + c0 + 32 * half + 4 * j, pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
         }
         st_shared_f32(red_sum + 2 * par, s0 + s1);
-        fence_proxy_async();                  // P (generic-proxy writes) -> visible to the tensor core's smem reads
+        tmem_st_wait();                       // P is in tensor memory (A operand of P·V)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
@@ -406,10 +405,10 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
   int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
   if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
   if (rc) return rc;
-  const int buf_bytes = 3 * NK * 128, p_bytes = ((NK + 63) / 64) * TILE, aux = 6144 + 128;
+  const int buf_bytes = 3 * NK * 128, aux = 6144 + 128;
   int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
-  while (nbuf > 1 && nbuf * buf_bytes + p_bytes + aux > kMaxDynSmem) --nbuf;
-  const int smem = nbuf * buf_bytes + p_bytes + aux;
+  while (nbuf > 1 && nbuf * buf_bytes + aux > kMaxDynSmem) --nbuf;
+  const int smem = nbuf * buf_bytes + aux;
   FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
   const int items = B * H;
   const int sms = fc_num_sms(device);
