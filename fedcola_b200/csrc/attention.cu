@@ -1,296 +1,765 @@
-// Fused short-sequence attention, forward and backward, head_dim = 64 (every reference factory:
-// 192/3, 384/6, 768/12 — /root/reference/src/models/mome.py:937-1030).
+// tcgen05 fused short-sequence attention, forward (head_dim 64, N <= 256 tokens).
 //
-// Replaces Attention.forward between the qkv and proj Linears (mome.py:153-165): q*scale, fp32 QK^T,
-// fp32 softmax, cast, P·V, head merge — and its autograd.  No attention mask exists in the reference
-// (pad tokens are attended); only the padding rows/columns this kernel adds to reach a
-// multiple of 16 are masked.  One CTA per (sample, head); the whole head (N <= 256 tokens) lives in
-// shared memory, so the [B,H,N,N] probability tensor is never materialised in HBM.
-//
-// This file holds the BACKWARD: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix from
-// swizzled shared memory (round-1 implementation; its tcgen05 rewrite is the next step).  The forward is the
-// tcgen05/TMEM kernel in attention_tc.cu.
+// Replaces Attention.forward between the qkv and proj Linears (/root/reference/src/models/mome.py:153-165):
+// q*scale, fp32 QK^T, fp32 softmax, cast, P·V, head merge.  Persistent CTAs (one per SM, 16 warps) walk the
+// (sample, head) items:
+//   TMA (3-D tensor maps over qkv [B, N, 3*H*64], 128-byte swizzle) stages Q, K, V of an item in shared memory —
+//   token rows >= N are zero-filled by the TMA unit; the next item is prefetched into a second buffer;
+//   S = Q K^T   : tcgen05.mma  M=128 queries, N=NK (keys padded to 16), K=64      -> TMEM (double-buffered, col 0/256)
+//   softmax     : TMEM lane = query row; the 4 warps of a lane quarter split the key columns 64 each, keep their
+//                 scores in registers (one tcgen05.ld pass), exchange row max / row sum through smem, and write
+//                 the normalised bf16 P tile (swizzled, K-major) for the second MMA;
+//   O = P V     : tcgen05.mma  M=128, N=64, K=NK (A = P K-major, B = V MN-major)  -> overlays the consumed S
+//   epilogue    : O -> bf16 -> 32-byte row segments straight to global (rows >= N skipped);
+//                 LSE = max + log(sum) for the backward.
 #include "common.cuh"
+#include "sm100.cuh"
 #include "../../include/fedcola_b200.h"
+
+#include <cstring>
+#include <mutex>
 
 namespace {
 
-constexpr int HD = 64;        // head dim
-constexpr int LDS = 64;       // smem row = 128 B = 8 chunks of 16 B, XOR-swizzled by (row & 7): conflict-free ldmatrix
-                              // without padding, so the backward kernel's 4 staged matrices fit twice per SM
+using namespace sm100;
 
-// element offset of 16-byte chunk `chunk` (0..7) of row r
-__device__ __forceinline__ int swz(int r, int chunk) { return r * LDS + ((chunk ^ (r & 7)) << 3); }
+constexpr int HD = 64;
+constexpr int TILE = 128 * 128;            // bytes of one 128-row x 128-byte swizzled tile (16 KB)
+#ifdef FC_ATTN_PROF
+__device__ long long g_attn_prof[16 * 12];
+#define PROF(slot) do { if (threadIdx.x == 0 && T < 16) prof_s[T * 12 + (slot)] = clock64(); } while (0)
+#else
+#define PROF(slot) do { } while (0)
+#endif
+#ifdef FC_ATTN_PROF
+constexpr int kMaxDynSmem = 232448 - 2048;
+#else
+constexpr int kMaxDynSmem = 232448;
+#endif
+constexpr int kSoftmaxWarps = 16;          // warp&3 = TMEM lane quarter (query rows), warp>>2 = 64-column group
+constexpr int kFwdThreads = (kSoftmaxWarps + 1) * 32;   // + one control warp (TMA producer / MMA issuer)
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
-}
-// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_bf16(uint32_t addr, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+}
+__device__ __forceinline__ float ld_shared_bf16(uint32_t addr) {
+  uint16_t h;
+  asm volatile("ld.shared.b16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+__device__ __forceinline__ void ld_shared_f32x4(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// MN-major B operand made of ONE 64-wide block (V: rows = keys = K index, 128-byte rows of 64 head-dim values)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_desc(addr, 8192, 1024); }
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }
 
-// A-operand fragments of a 16-row tile (rows r0..r0+15) for all 4 k16 steps of the 64-wide head dim.
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* s, int r0, int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) ldsm_x4(a[kk], s + swz(r0 + (lane & 15), kk * 2 + (lane >> 4)));
-}
-// acc(16 x 16 cols [c0, c0+16)) = A(16 x 64) * M[c0..c0+16, 0..64)^T — M rows are the "n" index, head dim is k.
-__device__ __forceinline__ void mma_rowsT(float (&acc)[2][4], const uint32_t (&a)[4][4], const __nv_bfloat16* m, int c0,
-                                          int lane) {
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-#pragma unroll
-    for (int kk = 0; kk < 4; kk += 2) {
-      uint32_t b[4];   // (n-tile j) x (k steps kk, kk+1)
-      ldsm_x4(b, m + swz(c0 + j * 8 + (lane & 7), kk * 2 + (lane >> 3)));
-      mma16816(acc[j], a[kk], b[0], b[1]);
-      mma16816(acc[j], a[kk + 1], b[2], b[3]);
-    }
-  }
-}
-// out(16 x 64) += P(16 x 16, as A fragments) * M[r0..r0+16, 0..64)  — M rows are the k index (needs .trans)
-__device__ __forceinline__ void mma_rows(float (&out)[8][4], const uint32_t (&p)[4], const __nv_bfloat16* m, int r0,
-                                         int lane) {
-#pragma unroll
-  for (int n = 0; n < 8; n += 2) {
-    uint32_t b[4];
-    ldsm_x4_t(b, m + swz(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, n + (lane >> 4)));
-    mma16816(out[n], p, b[0], b[1]);
-    mma16816(out[n + 1], p, b[2], b[3]);
-  }
-}
+struct FwdMaps {
+  CUtensorMap qkv_a, qkv_b;                  // box rows RA (first 128-token tile) / RB (remainder tile)
+};
 
-__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long row_stride, int n,
-                                           int npad) {
-  // 64 bf16 per row = 8 x 16 B; zero-fill padding rows
-  for (int i = threadIdx.x; i < npad * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < n) v = *reinterpret_cast<const uint4*>(src + (size_t)r * row_stride + c * 8);
-    *reinterpret_cast<uint4*>(dst + swz(r, c)) = v;
-  }
-}
-
-// Column sums over the 16 rows of a warp tile of two packed bf16 pairs (rows g and g+8, columns 2t, 2t+1):
-// reduce over the 8 row groups with shuffles, then lanes 0..3 add into shared memory.
-__device__ __forceinline__ void tile_colsum(float* dst, uint32_t w0, uint32_t w1, int lane) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
-  float x = a.x + b.x, y = a.y + b.y;
-#pragma unroll
-  for (int o = 4; o <= 16; o <<= 1) {
-    x += __shfl_xor_sync(0xffffffffu, x, o);
-    y += __shfl_xor_sync(0xffffffffu, y, o);
-  }
-  if (lane < 4) {
-    atomicAdd(dst, x);
-    atomicAdd(dst + 1, y);
-  }
-}
-
-// ---- backward -----------------------------------------------------------------------------------
-// dV = P^T dO;  dP = dO V^T;  dS = P ⊙ (dP - D), D_i = sum_c dO_ic O_ic;  dQ = scale dS K;  dK = scale dS^T Q
-template <int NPAD, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                       const __nv_bfloat16* __restrict__ o_fwd,
-                                                       const __nv_bfloat16* __restrict__ d_out,
-                                                       const float* __restrict__ lse_g,
-                                                       __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
-                                                       int N, int H, float scale) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* Ks = Qs + NPAD * LDS;
-  __nv_bfloat16* Vs = Ks + NPAD * LDS;
-  __nv_bfloat16* Gs = Vs + NPAD * LDS;                       // dO
-  float* lse = reinterpret_cast<float*>(Gs + NPAD * LDS);    // [NPAD]
-  float* Dr = lse + NPAD;                                    // [NPAD]
-  float* s_db = Dr + NPAD;                                   // [3*64] column sums of dQ | dK | dV of this head
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+// Persistent: CTA c handles (sample, head) items c, c+grid, ...  Warp 16 is the control warp: its lane 0 prefetches
+// the next items' Q/K/V by TMA (nbuf smem buffers) and issues every tcgen05.mma; warps 0-15 do the softmax and the
+// output.  S accumulators are double-buffered in TMEM (columns 0 / 256) and O overlays its own consumed S, so
+// QK^T of tile T+1 and P·V of tile T run under the softmax warps' work on the neighbouring tiles.
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                   int n_items, int N, int H, int nbuf, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
+#ifdef FC_ATTN_PROF
+  __shared__ long long prof_s[16 * 12];
+#endif
+  if (smem_u32(smem) & 1023) __trap();
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;                     // keys padded to the UMMA N granularity; rows >= N are TMA zero fill
+  const int q_tiles = RB ? 2 : 1;
+  const int op_bytes = NK * 128;              // one operand (Q, K or V) of one item
+  const int buf_bytes = 3 * op_bytes;
+  // reduction scratch, double-buffered by tile parity: row-sum partials float [2][4][128], then row-max partials
+  // bf16 [2][4][128] (softmax is shift-invariant: a rounded max only has to be the SAME for the whole row)
+  uint8_t* red_base = smem + nbuf * buf_bytes;
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(red_base + 6144);    // [4] item operands landed
+  uint64_t* s_full = tma_bar + 4;                                      // [2] S buffer written by the tensor core
+  uint64_t* o_full = s_full + 2;                                       //     O written (and P, V no longer read)
+  uint64_t* p_full = o_full + 1;                                       //     P tile written by the 16 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
   const int d = H * HD;
-  const long long rs = 3LL * d;
-  const __nv_bfloat16* base = qkv + (size_t)b * N * rs + h * HD;
-  const __nv_bfloat16* gb = d_out + (size_t)b * N * d + h * HD;
-  const __nv_bfloat16* ofb = o_fwd + (size_t)b * N * d + h * HD;
-  stage_rows(Qs, base, rs, N, NPAD);
-  stage_rows(Ks, base + d, rs, N, NPAD);
-  stage_rows(Vs, base + 2 * d, rs, N, NPAD);
-  stage_rows(Gs, gb, d, N, NPAD);
-  for (int r = threadIdx.x; r < NPAD; r += blockDim.x) lse[r] = r < N ? lse_g[((size_t)b * H + h) * N + r] : INFINITY;
-  for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x) s_db[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&tma_bar[i], 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(o_full, 1);
+    mbar_init(p_full, kSoftmaxWarps);
+    fence_barrier_init();
+  }
+  if (warp == kSoftmaxWarps) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
   __syncthreads();
-  // D_i = <dO_i, O_i>: 8 lanes per row, 8 elements each
-  for (int i = threadIdx.x; i < NPAD * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    float acc = 0.f;
-    if (r < N) {
-      const uint4 ov = *reinterpret_cast<const uint4*>(ofb + (size_t)r * d + c * 8);
-      const uint4 gv = *reinterpret_cast<const uint4*>(Gs + swz(r, c));
-      const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: NK <= 208: S0 [0,208) S1 [208,416) O [416,480); larger NK: one S buffer [0,256), O [256,320)
+  const int depth = NK <= 208 ? 2 : 1;
+  const uint32_t s_stride = 208, o_col = NK <= 208 ? 416 : 256;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+
+  if (warp == kSoftmaxWarps) {
+    // ================= control warp: TMA producer + MMA issuer (one lane) =================
+    if (lane == 0 && n_my > 0) {
+      prefetch_tmap(&maps.qkv_a);
+      prefetch_tmap(&maps.qkv_b);
+      const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      auto buf_addr = [&](int k) { return smem_u32(smem) + (k % nbuf) * buf_bytes; };
+      auto issue_load = [&](int k) {
+        const int item = first + k * stride;
+        const int b = item / H, h = item % H;
+        uint8_t* base = smem + (k % nbuf) * buf_bytes;
+        uint64_t* bar = &tma_bar[k % nbuf];
+        mbar_arrive_expect_tx(bar, buf_bytes);
+        for (int op = 0; op < 3; ++op) {      // Q, K, V column blocks of this head
+          tma_load_3d(base + op * op_bytes, &maps.qkv_a, bar, op * d + h * HD, 0, b);
+          if (RB) tma_load_3d(base + op * op_bytes + RA * 128, &maps.qkv_b, bar, op * d + h * HD, 128, b);
+        }
+      };
+      auto issue_s = [&](int k, int qt, int sbuf) {   // S[sbuf] = Q_tile K^T
+        if (qt == 0) mbar_wait(&tma_bar[k % nbuf], (k / nbuf) & 1);
+        tc_fence_after();
+        const uint32_t q = buf_addr(k) + qt * TILE, kk = buf_addr(k) + op_bytes;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = __bfloat1622float2(o2[k]), e = __bfloat1622float2(g2[k]);
-        acc += a.x * e.x + a.y * e.y;
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem + sbuf * s_stride, desc_k(q + j * 32), desc_k(kk + j * 32), idesc_s, j > 0);
+        umma_commit(&s_full[sbuf]);
+      };
+      // Issue order is a small state machine: loads run up to nbuf items ahead (a buffer is reusable once the last
+      // P·V of its item completed), QK^T runs up to `depth` tiles ahead of the softmax (an S buffer is reusable
+      // once the softmax warps consumed it, i.e. p_full of that tile), P·V follows p_full.
+      const int total = n_my * q_tiles;
+      int next_load = 0, next_s = 0, done_items = 0;
+      auto pump = [&](int T) {
+        while (next_load < n_my && next_load < done_items + nbuf) issue_load(next_load++);
+        while (next_s < total && next_s < T + depth && next_s / q_tiles < next_load) {
+          issue_s(next_s / q_tiles, next_s % q_tiles, next_s % depth);
+          ++next_s;
+        }
+      };
+      pump(0);
+      for (int T = 0; T < total; ++T) {
+        const int k = T / q_tiles;
+        while (!mbar_try_wait(p_full, T & 1)) __nanosleep(100);   // P_T in smem, S_T consumed, O_{T-1} read
+        tc_fence_after();
+        const uint32_t vv = buf_addr(k) + 2 * op_bytes;
+        const int ksteps = NK >> 4;
+        // P (bf16 pairs) sits in the S buffer: the 16 keys of k-step ks occupy 8 columns at 64*(ks/4) + 16*(ks%4) —
+        // each softmax warp packed its 32-score slabs in place (slab at +32*half, packed into its first 16 columns)
+        const uint32_t tP = tmem + (depth == 2 ? (T & 1) : 0) * s_stride;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), desc_mn(vv + ks * 2048),
+                       idesc_o, ks > 0);
+        umma_commit(o_full);
+        pump(T + 1);
+        if ((T + 1) % q_tiles == 0) {
+          mbar_wait(o_full, T & 1);           // every MMA reading buffer k % nbuf has completed
+          ++done_items;
+          pump(T + 1);
+        }
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (c == 0) Dr[r] = acc;
+  } else {
+    // ================= softmax warps =================
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int row = quarter * 32 + lane;      // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int c0 = grp * 64;
+    const int nc = min(max(NK - c0, 0), 64);  // columns of this warp (multiple of 16)
+    const int valid = min(nc, N - c0);        // ... of which real keys
+    const uint32_t red_sum = smem_u32(red_base) + (grp * 128 + row) * 4, red_sum_rd = smem_u32(red_base) + row * 4;
+    const uint32_t red_max = smem_u32(red_base) + 4096 + (grp * 128 + row) * 2;
+    const uint32_t red_max_rd = smem_u32(red_base) + 4096 + row * 2;
+    // one 32-wide (or trailing 16-wide) slab of this thread's score row; returns the number of columns loaded
+    auto load_slab = [&](uint32_t tS, int half, float (&v)[32]) -> int {
+      const int n = min(nc - 32 * half, 32);
+      if (n == 32) tmem_ld_32x32(tS + lane_off + c0 + 32 * half, v);
+      else if (n == 16) tmem_ld_32x16(tS + lane_off + c0 + 32 * half, *reinterpret_cast<float(*)[16]>(&v[0]));
+      tmem_ld_wait();
+      return n;
+    };
+    // O of a finished tile (columns [16*grp, +16) of this thread's row), scaled by that tile's 1/rowsum.  Loaded
+    // before this tile's P is published (the next P·V overwrites O), stored after it (a proxy fence behind
+    // outstanding global stores would wait for them).
+    auto load_o = [&](int T, float inv, uint32_t (&o)[8]) {
+      mbar_wait(o_full, T & 1);
+      tc_fence_after();
+      float f[16];
+      tmem_ld_32x16(tmem + o_col + lane_off + grp * 16, f);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack2(f[2 * i] * inv, f[2 * i + 1] * inv);
+    };
+    auto store_o = [&](const uint32_t (&o)[8], int bh_row0, int h, int qt) {
+      const int qrow = qt * 128 + row;
+      if (qrow < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(bh_row0) + qrow) * d + h * HD + grp * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    };
+    // keys >= N of a slab (columns at or beyond `nvalid`) -> -inf; only the slab holding the padding boundary
+    auto mask_slab = [&](float (&v)[32], int nvalid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
+    };
+    const float sc = scale_log2e;
+    // row sums of the previous tile -> 1/sum for its O rows, LSE for the backward
+    auto finish_sums = [&](int T, float mb, int bh, int qt) -> float {
+      const uint32_t rd = red_sum_rd + (T & 1) * 2048;
+      const float sum = (ld_shared_f32(rd) + ld_shared_f32(rd + 512)) + (ld_shared_f32(rd + 1024) + ld_shared_f32(rd + 1536));
+      const int qrow = qt * 128 + row;
+      if (grp == 0 && lse_out != nullptr && qrow < N)
+        lse_out[static_cast<size_t>(bh) * N + qrow] = 0.69314718056f * (mb + lg2(sum));
+      return rcp(sum);
+    };
+    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0;
+    float prev_mb = 0.f;
+    const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;   // item / H == (item * magic) >> 32 for item < 2^16
+    for (int k = 0, item = first; k < n_my; ++k, item += stride) {
+      const int b = static_cast<int>((static_cast<unsigned long long>(item) * h_magic) >> 32), h = item - b * H;
+      for (int qt = 0; qt < q_tiles; ++qt, ++T) {
+        const int sb = depth == 2 ? (T & 1) : 0;
+        const uint32_t tS = tmem + sb * s_stride;
+        const uint32_t par = (T & 1) * 1024;  // reduction scratch is double-buffered by tile parity: one barrier/tile
+        PROF(0);
+        mbar_wait(&s_full[sb], (depth == 2 ? (T >> 1) : T) & 1);
+        tc_fence_after();
+        PROF(1);
+        // ---- pass 1: row max over this warp's columns (keys >= N masked) ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (32 * half < nc) {                // warp-uniform
+            float v[32];
+            const int n = load_slab(tS, half, v);
+            if (32 * half + n > valid) mask_slab(v, valid - 32 * half);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (i < n) {
+                m0 = fmaxf(m0, v[i]);
+                m1 = fmaxf(m1, v[i + 1]);
+              }
+            }
+          }
+        }
+        st_shared_bf16(red_max + par, fmaxf(m0, m1));
+        softmax_warps_sync();                 // also: every warp has published the previous tile's row sums
+        PROF(3);
+        const float mx = fmaxf(fmaxf(ld_shared_bf16(red_max_rd + par), ld_shared_bf16(red_max_rd + par + 256)),
+                               fmaxf(ld_shared_bf16(red_max_rd + par + 512), ld_shared_bf16(red_max_rd + par + 768)));
+        const float mb = mx * sc, nmb = -mb;
+        // the previous tile's P·V ran under the work above: fetch its O now (this also frees the P tile)
+        uint32_t o[8];
+        if (T > 0) load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
+        PROF(4);
+        // ---- pass 2: p = exp2(s*c - max*c) -> bf16 -> swizzled K-major P tile (column block = grp); row sum ----
+        // P is left un-normalised (0 < p <= 1); the row of O is scaled by 1/sum in its epilogue.
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (32 * half < nc) {
+            float v[32];
+            const int n = load_slab(tS, half, v);
+            if (32 * half + n > valid) mask_slab(v, valid - 32 * half);   // exp2(-inf) = 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < n) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = 8 * j + 2 * e;
+                  const float p0 = ex2(fmaf(v[i], sc, nmb));
+                  const float p1 = ex2(fmaf(v[i + 1], sc, nmb));
+                  s0 += p0;
+                  s1 += p1;
+                  pk[e] = pack2(p0, p1);
+                }
+                // 8 keys -> 4 packed columns, written over this thread's own (already consumed) scores
+                tmem_st_32x4(tS + lane_off + c0 + 32 * half + 4 * j, pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+        st_shared_f32(red_sum + 2 * par, s0 + s1);
+        tmem_st_wait();                       // P is in tensor memory (A operand of P·V)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        PROF(5);
+        if (T > 0) store_o(o, prev_row0, prev_h, prev_qt);
+        prev_mb = mb;
+        prev_row0 = b * N;
+        prev_bh = item;
+        prev_h = h;
+        prev_qt = qt;
+        PROF(6);
+      }
+    }
+    if (T > 0) {
+      softmax_warps_sync();                   // last tile's row sums
+      uint32_t o[8];
+      load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
+      store_o(o, prev_row0, prev_h, prev_qt);
+    }
   }
+  tc_fence_before();
   __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  constexpr int NT = NPAD / 16;
-  const int nwarps = blockDim.x >> 5;
-  __nv_bfloat16* dq_base = dqkv + (size_t)b * N * rs + h * HD;
-
-  // ---- pass A: query tiles -> dQ ----
-  for (int mt = warp; mt < NT; mt += nwarps) {
-    uint32_t qa[4][4], ga[4][4];
-    load_a_frags(qa, Qs, mt * 16, lane);
-    load_a_frags(ga, Gs, mt * 16, lane);
-    const int row0 = mt * 16 + g, row1 = row0 + 8;
-    const float l0 = lse[row0], l1 = lse[row1], d0 = Dr[row0], d1 = Dr[row1];
-    float dq[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dq[n][i] = 0.f;
-#pragma unroll 1
-    for (int ct = 0; ct < NT; ++ct) {
-      float s[2][4], dp[2][4];
-      mma_rowsT(s, qa, Ks, ct * 16, lane);
-      mma_rowsT(dp, ga, Vs, ct * 16, lane);
-      uint32_t ds[4];
-      float v[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = ct * 16 + j * 8 + 2 * t + (i & 1);
-          const float p = col < N ? __expf(s[j][i] * scale - (i < 2 ? l0 : l1)) : 0.f;
-          v[j][i] = p * (dp[j][i] - (i < 2 ? d0 : d1));
-        }
-      ds[0] = pack2(v[0][0], v[0][1]); ds[1] = pack2(v[0][2], v[0][3]);
-      ds[2] = pack2(v[1][0], v[1][1]); ds[3] = pack2(v[1][2], v[1][3]);
-      mma_rows(dq, ds, Ks, ct * 16, lane);
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const uint32_t w0 = pack2(dq[n][0] * scale, dq[n][1] * scale), w1 = pack2(dq[n][2] * scale, dq[n][3] * scale);
-      if (row0 < N) *reinterpret_cast<uint32_t*>(dq_base + (size_t)row0 * rs + n * 8 + 2 * t) = w0;
-      if (row1 < N) *reinterpret_cast<uint32_t*>(dq_base + (size_t)row1 * rs + n * 8 + 2 * t) = w1;
-      if (dbias != nullptr) tile_colsum(s_db + n * 8 + 2 * t, row0 < N ? w0 : 0u, row1 < N ? w1 : 0u, lane);
-    }
-  }
-
-  // ---- pass B: key tiles -> dK, dV (transposed scores: rows = keys, columns = queries) ----
-  for (int jt = warp; jt < NT; jt += nwarps) {
-    uint32_t ka[4][4], va[4][4];
-    load_a_frags(ka, Ks, jt * 16, lane);
-    load_a_frags(va, Vs, jt * 16, lane);
-    const int key0 = jt * 16 + g, key1 = key0 + 8;
-    float dk[8][4], dv[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dk[n][i] = dv[n][i] = 0.f;
-#pragma unroll 1
-    for (int it = 0; it < NT; ++it) {
-      float s[2][4], dp[2][4];
-      mma_rowsT(s, ka, Qs, it * 16, lane);      // S^T tile: (key, query)
-      mma_rowsT(dp, va, Gs, it * 16, lane);     // dP^T tile
-      float pv[2][4], dsv[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = it * 16 + j * 8 + 2 * t + (i & 1);      // query index = column
-          const int key = (i < 2) ? key0 : key1;
-          const float p = (key < N) ? __expf(s[j][i] * scale - lse[q]) : 0.f;   // lse[q >= N] = +inf -> 0
-          pv[j][i] = p;
-          dsv[j][i] = p * (dp[j][i] - Dr[q]);
-        }
-      uint32_t pf[4], df[4];
-      pf[0] = pack2(pv[0][0], pv[0][1]); pf[1] = pack2(pv[0][2], pv[0][3]);
-      pf[2] = pack2(pv[1][0], pv[1][1]); pf[3] = pack2(pv[1][2], pv[1][3]);
-      df[0] = pack2(dsv[0][0], dsv[0][1]); df[1] = pack2(dsv[0][2], dsv[0][3]);
-      df[2] = pack2(dsv[1][0], dsv[1][1]); df[3] = pack2(dsv[1][2], dsv[1][3]);
-      mma_rows(dv, pf, Gs, it * 16, lane);
-      mma_rows(dk, df, Qs, it * 16, lane);
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const uint32_t k0 = pack2(dk[n][0] * scale, dk[n][1] * scale), k1 = pack2(dk[n][2] * scale, dk[n][3] * scale);
-      const uint32_t v0 = pack2(dv[n][0], dv[n][1]), v1 = pack2(dv[n][2], dv[n][3]);
-      if (key0 < N) {
-        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key0 * rs + n * 8 + 2 * t) = k0;
-        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key0 * rs + n * 8 + 2 * t) = v0;
-      }
-      if (key1 < N) {
-        *reinterpret_cast<uint32_t*>(dq_base + d + (size_t)key1 * rs + n * 8 + 2 * t) = k1;
-        *reinterpret_cast<uint32_t*>(dq_base + 2 * d + (size_t)key1 * rs + n * 8 + 2 * t) = v1;
-      }
-      if (dbias != nullptr) {
-        tile_colsum(s_db + HD + n * 8 + 2 * t, key0 < N ? k0 : 0u, key1 < N ? k1 : 0u, lane);
-        tile_colsum(s_db + 2 * HD + n * 8 + 2 * t, key0 < N ? v0 : 0u, key1 < N ? v1 : 0u, lane);
-      }
-    }
-  }
-  if (dbias != nullptr) {     // one global atomic per column per head: qkv bias gradient [3][H][64]
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x)
-      atomicAdd(dbias + (i / HD) * d + h * HD + (i % HD), s_db[i]);
+#ifdef FC_ATTN_PROF
+  if (blockIdx.x == 0 && threadIdx.x < 16 * 12) g_attn_prof[threadIdx.x] = prof_s[threadIdx.x];
+#endif
+  if (warp == kSoftmaxWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
-template <int NPAD>
-int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse,
-               __nv_bfloat16* dqkv, float* dbias, int B, int N, int H, float scale, cudaStream_t st) {
-  const int smem = 4 * NPAD * LDS * 2 + 2 * NPAD * 4 + 3 * HD * 4;
-  // warps per CTA chosen so the NPAD/16 row tiles split evenly (13 tiles -> 7 warps x 2 rounds)
-  constexpr int NW = NPAD == 208 ? 7 : (NPAD == 256 ? 8 : 4);
-  FC_SMEM_OPT_IN((attn_bwd_kernel<NPAD, NW>), smem);
-  attn_bwd_kernel<NPAD, NW><<<B * H, NW * 32, smem, st>>>(qkv, o, dout, lse, dqkv, dbias, N, H, scale);
-  FC_LAUNCH_CHECK();
+// =====================================================================================================
+// Backward.  Per (sample, head) item, in the S^T orientation (TMEM lane = key row, columns = queries):
+//   for each 128-key tile kt, for each 64-query chunk qc:
+//     S^T  = K[kt] Q[qc]^T, dP^T = V[kt] dO[qc]^T                      (tcgen05, SS)   -> TMEM chunk buffer (x2)
+//     P^T  = exp2(S^T*c - lse2[q]),  dS^T = P^T ∘ (dP^T - D[q])         (16 warps; lane = key, 16 columns each)
+//            P^T (bf16 pairs) is written back over the thread's own S^T columns, dS^T to a swizzled smem tile
+//     dV[kt] += P^T dO[qc]                                             (tcgen05, A from TMEM, B = dO MN-major)
+//     per pair of chunks (128 queries):
+//     dK[kt] += dS^T Q[pair]                                           (tcgen05, SS, B = Q MN-major)
+//     dQ[pair] += dS K[kt]                                             (tcgen05, SS, A = dS^T tile read MN-major)
+//   dV/dK leave TMEM after each key tile, dQ (2 x 64 columns) after the item; 1/sqrt(d) is applied there.
+// TMEM columns: chunk buffers 2 x (64 S^T + 64 dP^T) = [0,256), dV [256,320), dK [320,384), dQ [384,512).
+// D[q] = <dO[q], O[q]> and lse2[q] = lse[q]*log2(e) are computed from global memory one item ahead.
+// The qkv bias gradient (column sums of dqkv) is taken by fc_colsum_bf16 afterwards.
+constexpr int kBwdThreads = (kSoftmaxWarps + 1) * 32;
+constexpr int kRing = 4;                   // dS^T tiles (64 queries each): two pairs in flight
+
+struct BwdMaps {
+  CUtensorMap qkv_a, qkv_b, do_a, do_b;      // box rows RA / RB
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __restrict__ o_g,
+                   const __nv_bfloat16* __restrict__ do_g, const float* __restrict__ lse_g,
+                   __nv_bfloat16* __restrict__ dqkv, int n_items, int N, int H, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;                     // padded tokens (rows >= N are TMA zero fill)
+  const int nkt = RB ? 2 : 1;                 // key tiles
+  const int nqc = (NK + 63) >> 6;             // query chunks per key tile
+  const int op_bytes = NK * 128;
+  // smem: Q | K | V | dO | dS^T ring | lse2,D vectors [2 items][2][256] | barriers
+  const uint32_t sQ = smem_u32(smem), sK = sQ + op_bytes, sV = sK + op_bytes, sDO = sV + op_bytes;
+  const uint32_t sRing = sDO + op_bytes;
+  uint8_t* vec_base = smem + 4 * op_bytes + kRing * TILE;
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(vec_base + 4096);
+  uint64_t* sdp_full = tma_bar + 1;           // [2] S^T/dP^T chunk buffer written
+  uint64_t* e_done = sdp_full + 2;            // [2] chunk consumed: P^T in TMEM, dS^T in smem          (16 arrivals)
+  uint64_t* pair_done = e_done + 2;           // [2] dK/dQ (and every earlier MMA) of a pair completed
+  uint64_t* acc_free = pair_done + 2;         //     dV/dK of a key tile read out of TMEM                (16 arrivals)
+  uint64_t* dq_free = acc_free + 1;           //     dQ of an item read out of TMEM                      (16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+  const int d = H * HD, d3 = 3 * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(tma_bar, 1);
+    mbar_init(&sdp_full[0], 1);
+    mbar_init(&sdp_full[1], 1);
+    mbar_init(&e_done[0], kSoftmaxWarps);
+    mbar_init(&e_done[1], kSoftmaxWarps);
+    mbar_init(&pair_done[0], 1);
+    mbar_init(&pair_done[1], 1);
+    mbar_init(acc_free, kSoftmaxWarps);
+    mbar_init(dq_free, kSoftmaxWarps);
+    fence_barrier_init();
+  }
+  if (warp == kSoftmaxWarps) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+  const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;
+  auto item_bh = [&](int item, int& b, int& h) {
+    b = static_cast<int>((static_cast<unsigned long long>(item) * h_magic) >> 32);
+    h = item - b * H;
+  };
+
+  if (warp == kSoftmaxWarps) {
+    // ================= control warp: TMA producer + MMA issuer (one lane) =================
+    if (lane == 0 && n_my > 0) {
+      prefetch_tmap(&maps.qkv_a);
+      prefetch_tmap(&maps.qkv_b);
+      prefetch_tmap(&maps.do_a);
+      prefetch_tmap(&maps.do_b);
+      const uint32_t idesc_dv = umma_idesc_bf16(128, HD, 0, 1);    // A K-major (TMEM / dS^T tile), B MN-major
+      const uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // A = dS^T tile read MN-major, B MN-major
+      auto load_item = [&](int item, bool prefetch_only) {
+        int b, h;
+        item_bh(item, b, h);
+        if (!prefetch_only) mbar_arrive_expect_tx(tma_bar, 4 * op_bytes);
+        for (int op = 0; op < 4; ++op) {      // Q, K, V (columns of qkv), dO
+          const CUtensorMap* ma = op < 3 ? &maps.qkv_a : &maps.do_a;
+          const CUtensorMap* mb = op < 3 ? &maps.qkv_b : &maps.do_b;
+          const int col = (op < 3 ? op * d : 0) + h * HD;
+          if (prefetch_only) {
+            tma_prefetch_3d(ma, col, 0, b);
+            if (RB) tma_prefetch_3d(mb, col, 128, b);
+          } else {
+            tma_load_3d(smem + op * op_bytes, ma, tma_bar, col, 0, b);
+            if (RB) tma_load_3d(smem + op * op_bytes + RA * 128, mb, tma_bar, col, 128, b);
+          }
+        }
+      };
+      int cc = 0, pair = 0, tile_ctr = 0;     // global chunk / pair / key-tile counters
+      auto issue_sdp = [&](int lc, int gc) {  // chunk lc of the item -> chunk buffer gc & 1
+        const int kt = lc / nqc, qc = lc - kt * nqc;
+        const int W = min(64, NK - 64 * qc);
+        const uint32_t idesc = umma_idesc_bf16(128, W, 0, 0);
+        const uint32_t tb = tmem + (gc & 1) * 128;
+        const uint32_t kr = kt * TILE, qr = qc * 64 * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tb, desc_k(sK + kr + j * 32), desc_k(sQ + qr + j * 32), idesc, j > 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tb + 64, desc_k(sV + kr + j * 32), desc_k(sDO + qr + j * 32), idesc, j > 0);
+        umma_commit(&sdp_full[gc & 1]);
+      };
+      const int chunks = nkt * nqc;
+      for (int k = 0; k < n_my; ++k) {
+        if (k > 0) mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);   // operands of item k-1 are dead
+        load_item(first + k * stride, false);
+        if (k + 1 < n_my) load_item(first + (k + 1) * stride, true);
+        mbar_wait(tma_bar, k & 1);
+        tc_fence_after();
+        issue_sdp(0, cc);
+        if (chunks > 1) issue_sdp(1, cc + 1);
+        for (int lc = 0; lc < chunks; ++lc, ++cc) {
+          const int kt = lc / nqc, qc = lc - kt * nqc;
+          const int W = min(64, NK - 64 * qc);
+          mbar_wait(&e_done[cc & 1], (cc >> 1) & 1);
+          tc_fence_after();
+          if (qc == 0 && tile_ctr > 0) mbar_wait(acc_free, (tile_ctr - 1) & 1);   // dV/dK of the previous tile read
+          // dV[kt] += P^T dO[chunk]   (A: packed P^T in this chunk's S^T columns, 8 columns per 16 queries)
+          const uint32_t tb = tmem + (cc & 1) * 128;
+          for (int j = 0; j < (W >> 4); ++j)
+            umma_bf16_ts(tDV, tb + 16 * j, desc_mn(sDO + (64 * qc + 16 * j) * 128), idesc_dv, (qc | j) != 0);
+          if ((qc & 1) || qc == nqc - 1) {    // a pair of chunks (<= 128 queries) is complete
+            const int qt = qc >> 1, q0 = qt * 128;
+            const int wp = min(128, NK - q0);
+            const uint32_t tiles = sRing + (pair & 1) * 2 * TILE;
+            for (int j = 0; j < (wp >> 4); ++j)   // dK[kt] += dS^T Q[pair]
+              umma_bf16(tDK, desc_k(tiles + (j >> 2) * TILE + (j & 3) * 32), desc_mn(sQ + (q0 + 16 * j) * 128), idesc_dv,
+                        (qt | j) != 0);
+            if (kt == 0 && qt == 0 && k > 0) mbar_wait(dq_free, (k - 1) & 1);     // dQ of the previous item read
+            const int ksteps = (kt == 0 ? RA : RB) >> 4;
+            for (int j = 0; j < ksteps; ++j)      // dQ[pair] += dS K[kt]   (A MN-major: 2 blocks of 64 queries)
+              umma_bf16(tDQ + 64 * qt, umma_smem_desc(tiles + j * 2048, TILE, 1024),
+                        desc_mn(sK + (kt * 128 + 16 * j) * 128), idesc_dq, (kt | j) != 0);
+            umma_commit(&pair_done[pair & 1]);
+            ++pair;
+          }
+          if (lc + 2 < chunks) issue_sdp(lc + 2, cc + 2);   // same buffer: ordered behind dV above in the MMA pipe
+          if (qc == nqc - 1) ++tile_ctr;
+        }
+      }
+    }
+  } else {
+    // ================= elementwise warps =================
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int row = quarter * 32 + lane;      // key row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t vec = smem_u32(vec_base);
+    const float sc = scale * 1.4426950408889634f;
+    // lse2 / D of an item -> vector buffer (item parity); one token per thread (<= 256 < 512 threads)
+    auto compute_vectors = [&](int k) {
+      const int t = threadIdx.x;
+      if (t < 256) {
+        int b, h;
+        item_bh(first + k * stride, b, h);
+        float l2 = INFINITY, dd = 0.f;        // padding queries: P = exp2(-inf) = 0
+        if (t < N) {
+          l2 = lse_g[(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
+          const uint4* po = reinterpret_cast<const uint4*>(o_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
+          const uint4* pg = reinterpret_cast<const uint4*>(do_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 a = po[i], g = pg[i];
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              dd = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), dd);
+              dd = fmaf(__uint_as_float(aw[e] & 0xFFFF0000u), __uint_as_float(gw[e] & 0xFFFF0000u), dd);
+            }
+          }
+        }
+        st_shared_f32(vec + (k & 1) * 2048 + t * 4, l2);
+        st_shared_f32(vec + (k & 1) * 2048 + 1024 + t * 4, dd);
+      }
+    };
+    // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv
+    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col) {
+      float f[16];
+      tmem_ld_32x16(tcol + lane_off + grp * 16, f);
+      tmem_ld_wait();
+      if (tok < N) {
+        uint4* dst = reinterpret_cast<uint4*>(dqkv + (static_cast<size_t>(b) * N + tok) * d3 + col + grp * 16);
+        dst[0] = make_uint4(pack2(f[0] * mul, f[1] * mul), pack2(f[2] * mul, f[3] * mul), pack2(f[4] * mul, f[5] * mul),
+                            pack2(f[6] * mul, f[7] * mul));
+        dst[1] = make_uint4(pack2(f[8] * mul, f[9] * mul), pack2(f[10] * mul, f[11] * mul),
+                            pack2(f[12] * mul, f[13] * mul), pack2(f[14] * mul, f[15] * mul));
+      }
+    };
+    if (n_my > 0) compute_vectors(0);
+    softmax_warps_sync();
+    int cc = 0, pair = 0;
+    int pend_kv = -1, pend_kv_pair = 0, pend_kv_item = 0;   // key tile whose dV/dK still sit in TMEM (-1: none)
+    int pend_dq_item = -1, pend_dq_pair = 0;                // item whose dQ still sits in TMEM
+    auto flush_pending = [&]() {
+      if (pend_kv >= 0) {
+        mbar_wait(&pair_done[pend_kv_pair & 1], (pend_kv_pair >> 1) & 1);
+        tc_fence_after();
+        int b, h;
+        item_bh(pend_kv_item, b, h);
+        const int key = pend_kv * 128 + row;
+        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD);
+        store_acc(tDK, scale, key, b, d + h * HD);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        pend_kv = -1;
+      }
+      if (pend_dq_item >= 0) {
+        mbar_wait(&pair_done[pend_dq_pair & 1], (pend_dq_pair >> 1) & 1);
+        tc_fence_after();
+        int b, h;
+        item_bh(pend_dq_item, b, h);
+        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free);
+        pend_dq_item = -1;
+      }
+    };
+    for (int k = 0; k < n_my; ++k) {
+      const int item = first + k * stride;
+      const uint32_t vl = vec + (k & 1) * 2048, vd = vl + 1024;
+      for (int kt = 0; kt < nkt; ++kt) {
+        for (int qc = 0; qc < nqc; ++qc, ++cc) {
+          const int W = min(64, NK - 64 * qc);
+          const uint32_t tb = tmem + (cc & 1) * 128 + lane_off;
+          // ring tile of this chunk; its previous user (pair - 2) must have been consumed by dK/dQ
+          if ((qc & 1) == 0 && pair >= 2) mbar_wait(&pair_done[pair & 1], ((pair >> 1) - 1) & 1);
+          mbar_wait(&sdp_full[cc & 1], (cc >> 1) & 1);
+          tc_fence_after();
+          if (16 * grp < W) {                 // warp-uniform
+            float s[16], dp[16];
+            tmem_ld_32x16(tb + 16 * grp, s);
+            tmem_ld_32x16(tb + 64 + 16 * grp, dp);
+            tmem_ld_wait();
+            const int q0 = 64 * qc + 16 * grp;
+            uint32_t pp[8], ds[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float l[4], dv[4];
+              ld_shared_f32x4(vl + (q0 + i) * 4, l);
+              ld_shared_f32x4(vd + (q0 + i) * 4, dv);
+              float p[4], g[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                p[e] = ex2(fmaf(s[i + e], sc, -l[e]));
+                g[e] = p[e] * (dp[i + e] - dv[e]);
+              }
+              pp[i >> 1] = pack2(p[0], p[1]);
+              pp[(i >> 1) + 1] = pack2(p[2], p[3]);
+              ds[i >> 1] = pack2(g[0], g[1]);
+              ds[(i >> 1) + 1] = pack2(g[2], g[3]);
+            }
+            tmem_st_32x8(tb + 16 * grp, pp);  // P^T over this thread's own (consumed) scores
+            const uint32_t tile = sRing + ((pair & 1) * 2 + (qc & 1)) * TILE;
+            const uint32_t rsw = (tile + row * 128) | ((row & 7) << 4);
+            sts_u4(rsw ^ ((2 * grp) << 4), ds[0], ds[1], ds[2], ds[3]);
+            sts_u4(rsw ^ ((2 * grp + 1) << 4), ds[4], ds[5], ds[6], ds[7]);
+            tmem_st_wait();
+            fence_proxy_async();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&e_done[cc & 1]);
+          flush_pending();                    // outputs of the previous key tile / item, now that this chunk is handed over
+          if ((qc & 1) || qc == nqc - 1) {
+            if (qc == nqc - 1) {
+              pend_kv = kt;
+              pend_kv_pair = pair;
+              pend_kv_item = item;
+              if (kt == nkt - 1) {
+                pend_dq_item = item;
+                pend_dq_pair = pair;
+              }
+            }
+            ++pair;
+          }
+          if (kt == 0 && qc == 0 && k + 1 < n_my) {   // next item's vectors, one item ahead
+            compute_vectors(k + 1);
+          }
+        }
+      }
+      softmax_warps_sync();                   // next item's vectors are visible to every warp
+    }
+    flush_pending();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kSoftmaxWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+// bf16 [B, N, width] row-major; box = 64 columns x `rows` token rows x 1 sample, 128-byte swizzle
+int make_tmap3(CUtensorMap* m, const void* ptr, int B, int N, int width, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)width * 2, (cuuint64_t)N * width * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FC_FAIL(FC_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed (%d)", (int)r);
   return FC_OK;
 }
 
 }  // namespace
 
+extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim,
+                                int device, void* stream) {
+  FC_REQUIRE(head_dim == HD, "fc_attention_fwd: head_dim must be 64 (got %d)", head_dim);
+  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
+             "fc_attention_fwd: unsupported shape B=%d N=%d H=%d", B, N, H);
+  FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "fc_attention_fwd: qkv/out must be 16-byte aligned");
+  FcDeviceGuard guard(device);
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;
+  FwdMaps maps;
+  int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
+  if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
+  if (rc) return rc;
+  const int buf_bytes = 3 * NK * 128, aux = 6144 + 128;
+  int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
+  while (nbuf > 1 && nbuf * buf_bytes + aux > kMaxDynSmem) --nbuf;
+  const int smem = nbuf * buf_bytes + aux;
+  FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
+  const int items = B * H;
+  const int sms = fc_num_sms(device);
+  const int waves = (items + sms - 1) / sms;
+  const int grid = (items + waves - 1) / waves;                  // balanced persistent grid (<= #SMs)
+  const float scale_log2e = 0.125f * 1.4426950408889634f;        // 64^-0.5 * log2(e)
+  attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      maps, static_cast<__nv_bfloat16*>(out), lse, items, N, H, nbuf, scale_log2e);
+  FC_LAUNCH_CHECK();
+  return FC_OK;
+}
+
+extern "C" int fc_colsum_bf16(const void* x, long long ld, int rows, int n, float* out, int device, void* stream);
+
 extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                                 float* dbias, int B, int N, int H, int head_dim, int device, void* stream) {
   FC_REQUIRE(head_dim == HD, "fc_attention_bwd: head_dim must be 64 (got %d)", head_dim);
-  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0, "fc_attention_bwd: unsupported shape B=%d N=%d H=%d", B, N, H);
+  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
+             "fc_attention_bwd: unsupported shape B=%d N=%d H=%d", B, N, H);
+  FC_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) |
+               reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
+             "fc_attention_bwd: tensors must be 16-byte aligned");
   FcDeviceGuard guard(device);
-  const float scale = 0.125f;
-  auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  auto o = reinterpret_cast<const __nv_bfloat16*>(out);
-  auto g = reinterpret_cast<const __nv_bfloat16*>(d_out);
-  auto dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N <= 48) return launch_bwd<48>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
-  if (N <= 64) return launch_bwd<64>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
-  if (N <= 208) return launch_bwd<208>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
-  return launch_bwd<256>(q, o, g, lse, dq, dbias, B, N, H, scale, st);
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;
+  BwdMaps maps;
+  int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
+  if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
+  if (!rc) rc = make_tmap3(&maps.do_a, d_out, B, N, H * HD, RA);
+  if (!rc) rc = make_tmap3(&maps.do_b, d_out, B, N, H * HD, RB ? RB : RA);
+  if (rc) return rc;
+  const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
+  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, smem);
+  const int items = B * H;
+  const int sms = fc_num_sms(device);
+  const int waves = (items + sms - 1) / sms;
+  const int grid = (items + waves - 1) / waves;
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      maps, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(d_out), lse,
+      static_cast<__nv_bfloat16*>(dqkv), items, N, H, 0.125f);
+  FC_LAUNCH_CHECK();
+  if (dbias != nullptr) return fc_colsum_bf16(dqkv, 3LL * H * HD, B * N, 3 * H * HD, dbias, device, stream);
+  return FC_OK;
 }

@@ -1,7 +1,7 @@
 // Stand-alone phase profile of the tcgen05 attention forward (clock64 stamps of CTA 0 / thread 0).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFC_ATTN_PROF -Ifedcola_b200/csrc \
 //        tools/attn_prof.cu fedcola_b200/csrc/api.cu -lcuda -o gpurun_out/attn_prof
-#include "../fedcola_b200/csrc/attention_tc.cu"
+#include "../fedcola_b200/csrc/attention.cu"
 #include <cstdio>
 #include <vector>
 int main(int argc, char** argv) {
