@@ -25,7 +25,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTileFloats = kThreads * 4;     // one float4 per thread: 1024 floats = 4 KB per source per tile
 constexpr int kStage = 64;                    // source entries staged in smem per pass
-constexpr int kUnroll = 8;                    // source loads in flight per thread (x 16 B)
+constexpr int kUnroll = 4;                    // source loads in flight per thread (x 16 B)
 
 struct AggParams {
   int mode, n_jobs, n_tiles;
@@ -53,7 +53,7 @@ __device__ __forceinline__ float fold1(float f, float l, float c) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) aggregate_kernel(const AggParams P) {
+__global__ void __launch_bounds__(kThreads, 4) aggregate_kernel(const AggParams P) {
   __shared__ const float* s_src[kStage];
   __shared__ int s_flag[kStage];
   __shared__ float s_scale[kStage];
@@ -174,7 +174,7 @@ extern "C" int fc_aggregate(int mode, int n_jobs, int n_tiles, const int* job_ti
   FcDeviceGuard guard(device);
   AggParams P{mode, n_jobs, n_tiles, job_tile_start, job_numel, job_nout, job_gin, job_gout, job_gscale,
               job_src_start, src_ptr, src_flag, scale_ptr, coef};
-  int grid = grid_ctas > 0 ? grid_ctas : fc_num_sms(device) * 6;   // 3 resident CTAs/SM x 2 waves
+  int grid = grid_ctas > 0 ? grid_ctas : fc_num_sms(device) * 8;   // 4 resident CTAs/SM x 2 waves
   if (grid > n_tiles) grid = n_tiles;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == FC_AGG_LERP)

@@ -751,7 +751,7 @@ extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_
   if (!rc) rc = make_tmap3(&maps.do_b, d_out, B, N, H * HD, RB ? RB : RA);
   if (rc) return rc;
   const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
-  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, smem);
+  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
   const int items = B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
