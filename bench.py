@@ -117,6 +117,9 @@ def _log(msg):
         sys.stderr.flush()
 
 
+PREWARM_THREADED = 3
+
+
 def run_ours(a):
     import torch.distributed as dist
     from fedcola_b200 import _lib
@@ -200,11 +203,14 @@ def run_ours(a):
     if sampler is not None:
         sampler.start()        # spawn nvidia-smi now (forking this process mid-run costs ~0.3 s of host time)
     l0 = L.fc_launch_count()
-    total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, a.warmup, sampler)
+    # Client worker threads run on their own CUDA streams: torch's caching allocator keeps one pool per stream, so
+    # a few extra untimed rounds let every (thread, stream) pool reach its steady size before the W warm-up rounds.
+    warm = a.warmup + (PREWARM_THREADED if a.threads > 1 else 0)
+    total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, warm, sampler)
     launches = (L.fc_launch_count() - l0)
     _log("timed rounds done")
     clocks = sampler.finish() if sampler is not None else None
-    launches_timed = int(launches * a.steps / (a.steps + a.warmup))
+    launches_timed = int(launches * a.steps / (a.steps + warm))
     value = samples / (total_ms / 1e3)
     phases = dict(timed_rounds.phases)
     per_round_ms = list(timed_rounds.per_round)
@@ -230,7 +236,7 @@ def run_ours(a):
     _log("GEMM profile round done")
     server2, _ = make_server("host")
     _log("server built (host-resident data)")
-    e2e_ms, e2e_samples, _, _ = timed_rounds(server2, a.steps, max(a.warmup, 1))
+    e2e_ms, e2e_samples, _, _ = timed_rounds(server2, a.steps, max(warm, 1))
     per_sample = {"img": 3 * 224 * 224 * 4 + 8, "txt": SEQ * 8 + 8, "img+txt": 3 * 224 * 224 * 4 + SEQ * 8}
     h2d = sum(per_sample[m] * N_PER_CLIENT * c for m, c in (("img", 3), ("txt", 3), ("img+txt", 2))) * n_gpus
     d2h = 16 * 8 * n_gpus
@@ -248,7 +254,8 @@ def run_ours(a):
                                    "B=112, E=1, seq_len 64, AdamW lr 1e-4, drop_path 0.1; step = one server.update()",
                        "samples_per_round": samples // a.steps, "precision": "bf16 operands / fp32 accumulate, fp32 "
                        "master weights+optimizer+aggregation", "l2": "inputs larger than L2 (GBs of activations and "
-                       "parameters per round)", "parallelism": f"clients sharded over {n_gpus} GPU(s)"},
+                       "parameters per round)", "parallelism": f"clients sharded over {n_gpus} GPU(s); {a.threads} client worker thread(s)/GPU "
+                                      f"(args.num_thread), each on its own CUDA stream"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_timed,
             "clocks": clocks,
@@ -350,7 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--threads", type=int, default=1, help="client worker threads per GPU (args.num_thread)")
+    ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     a = ap.parse_args()
     if a.impl == "reference":
