@@ -374,7 +374,8 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
 //   dV/dK leave TMEM after each key tile, dQ (2 x 64 columns) after the item; 1/sqrt(d) is applied there.
 // TMEM columns: chunk buffers 2 x (64 S^T + 64 dP^T) = [0,256), dV [256,320), dK [320,384), dQ [384,512).
 // D[q] = <dO[q], O[q]> and lse2[q] = lse[q]*log2(e) are computed from global memory one item ahead.
-// The qkv bias gradient (column sums of dqkv) is taken by fc_colsum_bf16 afterwards.
+// The qkv bias gradient (column sums of the stored dQ and dV; the K part is identically zero) is reduced in the
+// accumulator epilogues.
 constexpr int kBwdThreads = (kSoftmaxWarps + 1) * 32;
 constexpr int kRing = 4;                   // dS^T tiles (64 queries each): two pairs in flight
 
@@ -385,7 +386,8 @@ struct BwdMaps {
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __restrict__ o_g,
                    const __nv_bfloat16* __restrict__ do_g, const float* __restrict__ lse_g,
-                   __nv_bfloat16* __restrict__ dqkv, int n_items, int N, int H, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_items, int N, int H,
+                   float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   const int RA = N > 128 ? 128 : ((N + 15) & ~15);
@@ -548,17 +550,40 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         st_shared_f32(vec + (k & 1) * 2048 + 1024 + t * 4, dd);
       }
     };
-    // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv
-    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col) {
+    // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv.
+    // colsum (nullable): += the column sums of what was stored (the qkv bias gradient), reduced over the warp's
+    // 32 rows by a halving butterfly (16 shuffles for 16 columns) and one atomic per column and warp.
+    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col, float* colsum) {
       float f[16];
       tmem_ld_32x16(tcol + lane_off + grp * 16, f);
       tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack2(f[2 * i] * mul, f[2 * i + 1] * mul);
       if (tok < N) {
         uint4* dst = reinterpret_cast<uint4*>(dqkv + (static_cast<size_t>(b) * N + tok) * d3 + col + grp * 16);
-        dst[0] = make_uint4(pack2(f[0] * mul, f[1] * mul), pack2(f[2] * mul, f[3] * mul), pack2(f[4] * mul, f[5] * mul),
-                            pack2(f[6] * mul, f[7] * mul));
-        dst[1] = make_uint4(pack2(f[8] * mul, f[9] * mul), pack2(f[10] * mul, f[11] * mul),
-                            pack2(f[12] * mul, f[13] * mul), pack2(f[14] * mul, f[15] * mul));
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      if (colsum != nullptr) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {         // the stored (rounded) values; rows past the sequence count as 0
+          v[2 * i] = tok < N ? __uint_as_float(pk[i] << 16) : 0.f;
+          v[2 * i + 1] = tok < N ? __uint_as_float(pk[i] & 0xFFFF0000u) : 0.f;
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {    // lane-mask 16, 8, 4, 2: keep one half of the columns, add the partner's
+          const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const float send = hi ? v[j] : v[j + w];
+            const float keep = hi ? v[j + w] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+          }
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 1) == 0) atomicAdd(colsum + col + grp * 16 + (lane >> 1), v[0]);
       }
     };
     if (n_my > 0) compute_vectors(0);
@@ -573,8 +598,9 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         int b, h;
         item_bh(pend_kv_item, b, h);
         const int key = pend_kv * 128 + row;
-        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD);
-        store_acc(tDK, scale, key, b, d + h * HD);
+        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD, dbias);
+        // the K bias gradient is identically zero (softmax is invariant to a shift of the scores): nothing to add
+        store_acc(tDK, scale, key, b, d + h * HD, nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
@@ -585,7 +611,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         tc_fence_after();
         int b, h;
         item_bh(pend_dq_item, b, h);
-        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD);
+        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, dbias);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_free);
@@ -730,8 +756,6 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
   return FC_OK;
 }
 
-extern "C" int fc_colsum_bf16(const void* x, long long ld, int rows, int n, float* out, int device, void* stream);
-
 extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                                 float* dbias, int B, int N, int H, int head_dim, int device, void* stream) {
   FC_REQUIRE(head_dim == HD, "fc_attention_bwd: head_dim must be 64 (got %d)", head_dim);
@@ -758,8 +782,7 @@ extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_
   const int grid = (items + waves - 1) / waves;
   attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       maps, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(d_out), lse,
-      static_cast<__nv_bfloat16*>(dqkv), items, N, H, 0.125f);
+      static_cast<__nv_bfloat16*>(dqkv), dbias, items, N, H, 0.125f);
   FC_LAUNCH_CHECK();
-  if (dbias != nullptr) return fc_colsum_bf16(dqkv, 3LL * H * HD, B * N, 3 * H * HD, dbias, device, stream);
   return FC_OK;
 }

@@ -4,6 +4,8 @@
 // the final self.norm (eps 1e-6, :751-752) and their autograd.  The forward writes the bf16 operand the
 // following tcgen05 GEMM consumes; the backward adds into the running residual gradient and also emits the
 // DropPath-scaled bf16 copy that the next backward GEMM consumes, so no separate cast/scale kernel runs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/fedcola_b200.h"
 
@@ -96,8 +98,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int row = warp; row < rows; row += nwarps) {
     const float m = mean[row], r = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_row_stride);
-    float4 g[NV], xh[NV];
+    float4 g[NV], xh[NV], prev[NV];
     float s1 = 0.f, s2 = 0.f;
+    // every global load of the row (dy, x and the running dx) is issued before the two warp reductions: one
+    // memory round trip per row instead of two
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nvec && accumulate) prev[i] = reinterpret_cast<const float4*>(dx + (size_t)row * dx_row_stride)[c];
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
@@ -134,10 +144,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
         o.z = r * (g[i].z - m1 - xh[i].z * m2);
         o.w = r * (g[i].w - m1 - xh[i].w * m2);
         float4* dxr = reinterpret_cast<float4*>(dx + (size_t)row * dx_row_stride) + c;
-        if (accumulate) {
-          const float4 p = *dxr;
-          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-        }
+        o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w;
         *dxr = o;
         if (dxs) {
           const uint32_t w0 = pack2(o.x * sc, o.y * sc), w1 = pack2(o.z * sc, o.w * sc);
@@ -218,7 +225,8 @@ extern "C" int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row
   FcDeviceGuard guard(device);
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
-  const int cap = fc_num_sms(device) * 4;     // 4 CTAs/SM; one atomicAdd per column per CTA for dgamma/dbeta
+  static const int per_sm = getenv("FC_LN_BWD_CTAS_PER_SM") ? atoi(getenv("FC_LN_BWD_CTAS_PER_SM")) : 2;
+  const int cap = fc_num_sms(device) * per_sm;   // resident CTAs/SM (111 registers); one atomicAdd per column per CTA
   if (grid > cap) grid = cap;
   const size_t smem = (dgamma || dxs_colsum) ? sizeof(float) * 3 * wpb * d : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -90,7 +90,8 @@ long long fc_gemm_profile_collect(double* total_ms, double* total_flops);
  * ------------------------------------------------------------------------------------------------ */
 int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim, int device,
                      void* stream);
-/* dbias (nullable): fp32 [3*H*64] += column sums of dqkv (the qkv bias gradient) */
+/* dbias (nullable): fp32 [3*H*64] += the qkv bias gradient: column sums of the stored dQ and dV thirds; the K third is
+ * left untouched — it is identically zero because softmax is invariant to a shift of the scores */
 int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                      float* dbias, int B, int N, int H, int head_dim, int device, void* stream);
 
