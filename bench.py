@@ -216,9 +216,13 @@ def run_ours(a):
     per_round_ms = list(timed_rounds.per_round)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): one extra round with per-launch CUDA events ----
+    # (one client at a time: with several client streams in flight an event pair around a launch would also time
+    #  the other streams' kernels it waits behind)
     L.fc_gemm_profile(1)
     server.round += 1
+    threads, server.args.num_thread = server.args.num_thread, 1
     ids = server.update()
+    server.args.num_thread = threads
     torch.cuda.synchronize()
     import ctypes
     ms, fl = ctypes.c_double(0), ctypes.c_double(0)
