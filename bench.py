@@ -120,6 +120,17 @@ def _log(msg):
 PREWARM_THREADED = 3
 
 
+def _gemm_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu capture (profiles/r1_gemm_traffic.json), or (None, why)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return round(t["avg_dram_bytes_per_launch"]), t["source"] + " — image-client shapes, cold-cache replays"
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture committed"
+
+
 def run_ours(a):
     import torch.distributed as dist
     from fedcola_b200 import _lib
@@ -265,7 +276,7 @@ def run_ours(a):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(gemm_tflops, 2),
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(gemm_tflops / pk["tf_sustained"], 4),
-                         "peak_source": pk["src"] + " sustained bf16", "traffic": None,
+                         "peak_source": pk["src"] + " sustained bf16", "traffic": _gemm_traffic()[0], "traffic_source": _gemm_traffic()[1],
                          "launches_per_round": int(n_gemm), "avg_launch_us": round(ms.value * 1e3 / max(n_gemm, 1), 2),
                          "round_model_tflops": round(round_flops * n_gpus / (total_ms / a.steps * 1e-3) / 1e12 / n_gpus, 2)},
             "phase_ms_host_clock": {k: round(v, 2) for k, v in phases.items()},
