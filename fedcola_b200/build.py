@@ -13,7 +13,7 @@ STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("FC_PTXAS_V") else "-O3",
-         "-I", os.path.join(ROOT, "include")]
+         "-I", os.path.join(ROOT, "include")] + os.environ.get("FC_NVCC_EXTRA", "").split()   # e.g. -DFC_GEMM_EXP_STAGES=4
 
 
 def sources():

@@ -33,19 +33,27 @@ using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 16;              // four warps per TMEM lane quarter, interleaved 32-column chunks
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
+// Epilogue warps (per TMEM lane quarter: n/4 warps, interleaved column chunks).  The shared memory their staging
+// tiles do not take goes to the TMA ring, and at K = 384 the main loop is limited by the bytes the ring keeps in
+// flight per SM: epilogues with little arithmetic run 8 warps + one more stage (main loop 10-16 % faster), the
+// GELU / GELU'-multiply / patch epilogues need all 16 (measured with tools/gemm_bench.py).
+constexpr int epi_warps_for(int epi) {
+  return (epi == FC_EPI_GELU || epi == FC_EPI_MULAUX || epi == FC_EPI_PATCH) ? 16 : 8;
+}
+constexpr int gemm_threads_for(int epi) { return 64 + epi_warps_for(epi) * 32; }   // + TMA producer, MMA issuer
 constexpr int STAGE_LD = 36;               // floats per row of the legacy transpose buffer (PATCH epilogue only)
 constexpr int EPI_BUF_BYTES = 32 * 128;    // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store/load tile)
 constexpr int EPI_BIAS_BYTES = 64 * 4;      // per epilogue warp: the bias of the chunk's (up to) 64 columns
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * (EPI_BUF_BYTES + EPI_BIAS_BYTES);
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
-template <int BN> struct Cfg {
+template <int BN, int EPI> struct Cfg {
+  static constexpr int EPI_WARPS = epi_warps_for(EPI);
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * (EPI_BUF_BYTES + EPI_BIAS_BYTES);
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 3 : 4);   // what fits beside the epilogue staging
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  // what fits beside the epilogue staging
+  static constexpr int STAGES = EPI_WARPS == 8 ? (BN == 128 ? 5 : 4) : (BN == 128 ? 4 : 3);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 512 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
@@ -402,14 +410,16 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
 // smem ring (TMA -> MMA) runs across tile boundaries; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int A_MN, int B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads_for(EPI), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                  const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   constexpr int STAGES = C::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int EPI_WARPS = C::EPI_WARPS;
+  constexpr int EPI_STAGE_BYTES = C::EPI_STAGE_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
+  if (smem_u32(smem) & 1023) __trap();
   uint8_t* epi_stage = smem + STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -672,7 +682,7 @@ template <int BN, int A_MN, int B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int device,
            cudaStream_t st) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
-  FC_SMEM_OPT_IN(kern, Cfg<BN>::SMEM_BYTES);
+  FC_SMEM_OPT_IN(kern, (Cfg<BN, EPI>::SMEM_BYTES));
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = fc_num_sms(device);
   if (grid > total_tiles) grid = total_tiles;
@@ -683,7 +693,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
     cudaEventCreate(&rec.b);
     cudaEventRecord(rec.a, st);
   }
-  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
+  kern<<<grid, gemm_threads_for(EPI), Cfg<BN, EPI>::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
   if (prof) {
     cudaEventRecord(rec.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
