@@ -26,6 +26,7 @@ constexpr int kThreads = 256;
 constexpr int kTileFloats = kThreads * 4;     // one float4 per thread: 1024 floats = 4 KB per source per tile
 constexpr int kStage = 64;                    // source entries staged in smem per pass
 constexpr int kUnroll = 4;                    // source loads in flight per thread (x 16 B)
+constexpr int kRun = 8;                       // consecutive tiles a CTA takes at a time
 
 struct AggParams {
   int mode, n_jobs, n_tiles;
@@ -60,21 +61,39 @@ __global__ void __launch_bounds__(kThreads, 4) aggregate_kernel(const AggParams 
   __shared__ float s_coef[kStage][FC_AGG_MAX_OUT];
   __shared__ int s_job;
 
-  for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    // tile -> job: binary search over the tile prefix (n_jobs is a few hundred)
-    if (threadIdx.x == 0) {
-      int lo = 0, hi = P.n_jobs;            // invariant: start[lo] <= tile < start[hi]
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(P.job_tile_start + mid) <= tile) lo = mid; else hi = mid;
+  // A CTA takes runs of kRun consecutive tiles: consecutive tiles almost always belong to the same job, so the
+  // tile -> job search, the job's metadata and its staged source table are reused instead of being re-fetched
+  // through three dependent global-memory round trips per 4 KB tile (that chain, not bandwidth, bounded rounds
+  // with few clients per tensor).
+  const int n_runs = (P.n_tiles + kRun - 1) / kRun;
+  int job = -1, job_first = 0, job_end = 0, nout = 0, s0 = 0, s1 = 0;
+  long long numel = 0;
+  bool staged = false;                        // the smem table holds ALL sources of `job`
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+   const int tile_end = min(P.n_tiles, (run + 1) * kRun);
+   for (int tile = run * kRun; tile < tile_end; ++tile) {
+    if (job < 0 || tile >= job_end) {         // CTA-uniform
+      __syncthreads();                        // everyone is done with s_job and the staged table
+      // tile -> job: binary search over the tile prefix (n_jobs is a few hundred)
+      if (threadIdx.x == 0) {
+        int lo = 0, hi = P.n_jobs;            // invariant: start[lo] <= tile < start[hi]
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(P.job_tile_start + mid) <= tile) lo = mid; else hi = mid;
+        }
+        s_job = lo;
       }
-      s_job = lo;
+      __syncthreads();
+      job = s_job;
+      nout = P.job_nout[job];
+      numel = (P.job_numel[job] + 3) & ~3LL;  // segments are padded to 32 floats
+      job_first = P.job_tile_start[job];
+      job_end = P.job_tile_start[job + 1];
+      s0 = P.job_src_start[job];
+      s1 = P.job_src_start[job + 1];
+      staged = false;
     }
-    __syncthreads();
-    const int job = s_job;
-    const int nout = P.job_nout[job];
-    const long long numel = (P.job_numel[job] + 3) & ~3LL;      // segments are padded to 32 floats
-    const long long idx = (long long)(tile - P.job_tile_start[job]) * kTileFloats + threadIdx.x * 4;
+    const long long idx = (long long)(tile - job_first) * kTileFloats + threadIdx.x * 4;
     const bool active = idx < numel;
 
     float4 f[FC_AGG_MAX_OUT];
@@ -96,9 +115,9 @@ __global__ void __launch_bounds__(kThreads, 4) aggregate_kernel(const AggParams 
     }
     float4 pend = make_float4(0.f, 0.f, 0.f, 0.f);    // W of an aux-merged upload, waiting for its A entry
 
-    const int s0 = P.job_src_start[job], s1 = P.job_src_start[job + 1];
     for (int k0 = s0; k0 < s1; k0 += kStage) {
       const int kn = min(kStage, s1 - k0);
+      if (!staged) {
       __syncthreads();   // previous pass finished reading the staged table
       if (threadIdx.x < kn) {
         const int k = k0 + threadIdx.x;
@@ -110,6 +129,8 @@ __global__ void __launch_bounds__(kThreads, 4) aggregate_kernel(const AggParams 
         for (int o = 0; o < FC_AGG_MAX_OUT; ++o) s_coef[threadIdx.x][o] = P.coef[(size_t)k * FC_AGG_MAX_OUT + o];
       }
       __syncthreads();
+      staged = s1 - s0 <= kStage;             // a single pass: the table stays valid for the job's next tiles
+      }
       if (active) {
 #pragma unroll 1
         for (int k = 0; k < kn; k += kUnroll) {
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 4) aggregate_kernel(const AggParams 
       for (int o = 0; o < FC_AGG_MAX_OUT; ++o)
         if (o < nout) st_stream_f4(reinterpret_cast<float*>(P.job_gout[job * FC_AGG_MAX_OUT + o]) + idx, f[o]);
     }
-    __syncthreads();   // s_job / staged tables are reused by the next tile
+   }
   }
 }
 
@@ -175,7 +196,8 @@ extern "C" int fc_aggregate(int mode, int n_jobs, int n_tiles, const int* job_ti
   AggParams P{mode, n_jobs, n_tiles, job_tile_start, job_numel, job_nout, job_gin, job_gout, job_gscale,
               job_src_start, src_ptr, src_flag, scale_ptr, coef};
   int grid = grid_ctas > 0 ? grid_ctas : fc_num_sms(device) * 8;   // 4 resident CTAs/SM x 2 waves
-  if (grid > n_tiles) grid = n_tiles;
+  const int n_runs = (n_tiles + kRun - 1) / kRun;
+  if (grid > n_runs) grid = n_runs;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == FC_AGG_LERP)
     aggregate_kernel<FC_AGG_LERP><<<grid, kThreads, 0, st>>>(P);
