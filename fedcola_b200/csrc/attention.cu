@@ -1,17 +1,21 @@
-// tcgen05 fused short-sequence attention, forward (head_dim 64, N <= 256 tokens).
+// tcgen05 fused short-sequence attention, forward and backward (head_dim 64, N <= 256 tokens).
 //
-// Replaces Attention.forward between the qkv and proj Linears (/root/reference/src/models/mome.py:153-165):
-// q*scale, fp32 QK^T, fp32 softmax, cast, P·V, head merge.  Persistent CTAs (one per SM, 16 warps) walk the
-// (sample, head) items:
+// Replaces Attention.forward between the qkv and proj Linears (/root/reference/src/models/mome.py:153-165) —
+// q*scale, fp32 QK^T, fp32 softmax, cast, P·V, head merge — and its autograd.
+//
+// Forward.  Persistent CTAs (one per SM) walk the (sample, head) items; 16 softmax warps + 1 control warp whose
+// lane 0 is the TMA producer and the only tcgen05.mma issuer:
 //   TMA (3-D tensor maps over qkv [B, N, 3*H*64], 128-byte swizzle) stages Q, K, V of an item in shared memory —
-//   token rows >= N are zero-filled by the TMA unit; the next item is prefetched into a second buffer;
-//   S = Q K^T   : tcgen05.mma  M=128 queries, N=NK (keys padded to 16), K=64      -> TMEM (double-buffered, col 0/256)
-//   softmax     : TMEM lane = query row; the 4 warps of a lane quarter split the key columns 64 each, keep their
-//                 scores in registers (one tcgen05.ld pass), exchange row max / row sum through smem, and write
-//                 the normalised bf16 P tile (swizzled, K-major) for the second MMA;
-//   O = P V     : tcgen05.mma  M=128, N=64, K=NK (A = P K-major, B = V MN-major)  -> overlays the consumed S
-//   epilogue    : O -> bf16 -> 32-byte row segments straight to global (rows >= N skipped);
-//                 LSE = max + log(sum) for the backward.
+//   token rows >= N are zero-filled by the TMA unit; up to 4 items are in flight;
+//   S = Q K^T   : tcgen05.mma  M=128 queries, N=NK (keys padded to 16), K=64      -> TMEM, double-buffered
+//   softmax     : TMEM lane = query row; the 4 warps of a lane quarter split the key columns 64 each; pass 1 row
+//                 max, pass 2 exp2 + row sum, both straight out of TMEM; partial max/sum go through 6 KB of smem
+//                 with one named barrier per tile; the bf16 (un-normalised) P is written back over the S columns
+//                 it came from (tcgen05.st);
+//   O = P V     : tcgen05.mma  M=128, N=64, K=NK, A = P read from tensor memory, B = V MN-major from smem
+//   epilogue    : (one tile later, under the next tile's softmax) O / rowsum -> bf16 -> 32-byte row segments to
+//                 global (rows >= N skipped); LSE = max + log(sum) for the backward.
+// Backward: see the comment above attn_bwd_tc_kernel.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "../../include/fedcola_b200.h"
@@ -39,9 +43,6 @@ constexpr int kMaxDynSmem = 232448;
 constexpr int kSoftmaxWarps = 16;          // warp&3 = TMEM lane quarter (query rows), warp>>2 = 64-column group
 constexpr int kFwdThreads = (kSoftmaxWarps + 1) * 32;   // + one control warp (TMA producer / MMA issuer)
 
-__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
