@@ -89,6 +89,10 @@ __device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1,
 // MN-major B operand made of ONE 64-wide block (V: rows = keys = K index, 128-byte rows of 64 head-dim values)
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_desc(addr, 8192, 1024); }
 __device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024); }
+// The start-address field is the low 14 bits (address >> 4) and shared memory ends below 2^18 bytes, so a descriptor
+// for another address is the zero-address descriptor plus (address >> 4): the MMA issue loops below advance their
+// operands with one 64-bit add instead of rebuilding the descriptor (the single issuing thread is a bottleneck).
+__device__ __forceinline__ uint64_t desc_at(uint64_t zero_addr_desc, uint32_t addr) { return zero_addr_desc + (addr >> 4); }
 
 struct FwdMaps {
   CUtensorMap qkv_a, qkv_b;                  // box rows RA (first 128-token tile) / RB (remainder tile)
@@ -164,13 +168,14 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
           if (RB) tma_load_3d(base + op * op_bytes + RA * 128, &maps.qkv_b, bar, op * d + h * HD, 128, b);
         }
       };
+      const uint64_t dk0 = desc_k(0), dmn0 = desc_mn(0);
       auto issue_s = [&](int k, int qt, int sbuf) {   // S[sbuf] = Q_tile K^T
         if (qt == 0) mbar_wait(&tma_bar[k % nbuf], (k / nbuf) & 1);
         tc_fence_after();
-        const uint32_t q = buf_addr(k) + qt * TILE, kk = buf_addr(k) + op_bytes;
+        const uint64_t q = desc_at(dk0, buf_addr(k) + qt * TILE), kk = desc_at(dk0, buf_addr(k) + op_bytes);
+        const uint32_t ts = tmem + sbuf * s_stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16(tmem + sbuf * s_stride, desc_k(q + j * 32), desc_k(kk + j * 32), idesc_s, j > 0);
+        for (int j = 0; j < 4; ++j) umma_bf16(ts, q + 2 * j, kk + 2 * j, idesc_s, j > 0);   // 32 bytes per k-step
         umma_commit(&s_full[sbuf]);
       };
       // Issue order is a small state machine: loads run up to nbuf items ahead (a buffer is reusable once the last
@@ -190,14 +195,13 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
         const int k = T / q_tiles;
         while (!mbar_try_wait(p_full, T & 1)) __nanosleep(100);   // P_T in smem, S_T consumed, O_{T-1} read
         tc_fence_after();
-        const uint32_t vv = buf_addr(k) + 2 * op_bytes;
+        uint64_t vv = desc_at(dmn0, buf_addr(k) + 2 * op_bytes);
         const int ksteps = NK >> 4;
-        // P (bf16 pairs) sits in the S buffer: the 16 keys of k-step ks occupy 8 columns at 64*(ks/4) + 16*(ks%4) —
-        // each softmax warp packed its 32-score slabs in place (slab at +32*half, packed into its first 16 columns)
+        // P (bf16 pairs) sits in the S buffer: the 16 keys of k-step ks occupy 8 columns at 64*(ks/4) + 32*((ks/2)&1) +
+        // 8*(ks&1) — each softmax warp packed its 32-score slabs in place (slab at +32*half, packed into its first 16)
         const uint32_t tP = tmem + (depth == 2 ? (T & 1) : 0) * s_stride;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), desc_mn(vv + ks * 2048),
-                       idesc_o, ks > 0);
+        for (int ks = 0; ks < ksteps; ++ks, vv += 128)     // 16 key rows of V = 2048 bytes
+          umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), vv, idesc_o, ks > 0);
         umma_commit(o_full);
         pump(T + 1);
         if ((T + 1) % q_tiles == 0) {
@@ -467,16 +471,18 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         }
       };
       int cc = 0, pair = 0, tile_ctr = 0;     // global chunk / pair / key-tile counters
+      const uint64_t dk0 = desc_k(0), dmn0 = desc_mn(0), dq0 = umma_smem_desc(0, TILE, 1024);
+      const uint64_t dK = desc_at(dk0, sK), dQ = desc_at(dk0, sQ), dV = desc_at(dk0, sV), dDO = desc_at(dk0, sDO);
       auto issue_sdp = [&](int lc, int gc) {  // chunk lc of the item -> chunk buffer gc & 1
         const int kt = lc / nqc, qc = lc - kt * nqc;
         const int W = min(64, NK - 64 * qc);
         const uint32_t idesc = umma_idesc_bf16(128, W, 0, 0);
         const uint32_t tb = tmem + (gc & 1) * 128;
-        const uint32_t kr = kt * TILE, qr = qc * 64 * 128;
+        const uint32_t kr = (kt * TILE) >> 4, qr = (qc * 64 * 128) >> 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tb, desc_k(sK + kr + j * 32), desc_k(sQ + qr + j * 32), idesc, j > 0);
+        for (int j = 0; j < 4; ++j) umma_bf16(tb, dK + kr + 2 * j, dQ + qr + 2 * j, idesc, j > 0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tb + 64, desc_k(sV + kr + j * 32), desc_k(sDO + qr + j * 32), idesc, j > 0);
+        for (int j = 0; j < 4; ++j) umma_bf16(tb + 64, dV + kr + 2 * j, dDO + qr + 2 * j, idesc, j > 0);
         umma_commit(&sdp_full[gc & 1]);
       };
       const int chunks = nkt * nqc;
@@ -496,20 +502,27 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
           if (qc == 0 && tile_ctr > 0) mbar_wait(acc_free, (tile_ctr - 1) & 1);   // dV/dK of the previous tile read
           // dV[kt] += P^T dO[chunk]   (A: packed P^T in this chunk's S^T columns, 8 columns per 16 queries)
           const uint32_t tb = tmem + (cc & 1) * 128;
-          for (int j = 0; j < (W >> 4); ++j)
-            umma_bf16_ts(tDV, tb + 16 * j, desc_mn(sDO + (64 * qc + 16 * j) * 128), idesc_dv, (qc | j) != 0);
+          {
+            uint64_t b = desc_at(dmn0, sDO + 64 * qc * 128);
+            for (int j = 0; j < (W >> 4); ++j, b += 128) umma_bf16_ts(tDV, tb + 16 * j, b, idesc_dv, (qc | j) != 0);
+          }
           if ((qc & 1) || qc == nqc - 1) {    // a pair of chunks (<= 128 queries) is complete
             const int qt = qc >> 1, q0 = qt * 128;
             const int wp = min(128, NK - q0);
             const uint32_t tiles = sRing + (pair & 1) * 2 * TILE;
-            for (int j = 0; j < (wp >> 4); ++j)   // dK[kt] += dS^T Q[pair]
-              umma_bf16(tDK, desc_k(tiles + (j >> 2) * TILE + (j & 3) * 32), desc_mn(sQ + (q0 + 16 * j) * 128), idesc_dv,
-                        (qt | j) != 0);
+            {                                 // dK[kt] += dS^T Q[pair]
+              const uint64_t a = desc_at(dk0, tiles);
+              uint64_t b = desc_at(dmn0, sQ + q0 * 128);
+              for (int j = 0; j < (wp >> 4); ++j, b += 128)
+                umma_bf16(tDK, a + (j >> 2) * (TILE >> 4) + (j & 3) * 2, b, idesc_dv, (qt | j) != 0);
+            }
             if (kt == 0 && qt == 0 && k > 0) mbar_wait(dq_free, (k - 1) & 1);     // dQ of the previous item read
             const int ksteps = (kt == 0 ? RA : RB) >> 4;
-            for (int j = 0; j < ksteps; ++j)      // dQ[pair] += dS K[kt]   (A MN-major: 2 blocks of 64 queries)
-              umma_bf16(tDQ + 64 * qt, umma_smem_desc(tiles + j * 2048, TILE, 1024),
-                        desc_mn(sK + (kt * 128 + 16 * j) * 128), idesc_dq, (kt | j) != 0);
+            {                                 // dQ[pair] += dS K[kt]   (A MN-major: 2 blocks of 64 queries)
+              uint64_t a = desc_at(dq0, tiles), b = desc_at(dmn0, sK + kt * 128 * 128);
+              for (int j = 0; j < ksteps; ++j, a += 128, b += 128)
+                umma_bf16(tDQ + 64 * qt, a, b, idesc_dq, (kt | j) != 0);
+            }
             umma_commit(&pair_done[pair & 1]);
             ++pair;
           }
