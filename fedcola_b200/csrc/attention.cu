@@ -70,9 +70,6 @@ __device__ __forceinline__ float ld_shared_bf16(uint32_t addr) {
 __device__ __forceinline__ void ld_shared_f32x4(uint32_t addr, float (&v)[4]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void lds_u4(uint32_t addr, uint32_t (&v)[4]) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
-}
 __device__ __forceinline__ float lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -382,13 +379,13 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
 //   dV/dK leave TMEM after each key tile, dQ (2 x 64 columns) after the item; 1/sqrt(d) is applied there.
 // TMEM columns: chunk buffers 2 x (64 S^T + 64 dP^T) = [0,256), dV [256,320), dK [320,384), dQ [384,512).
 // D[q] = <dO[q], O[q]> and lse2[q] = lse[q]*log2(e) are computed from global memory one item ahead.
-// The qkv bias gradient (column sums of the stored dQ and dV; the K part is identically zero) is reduced in the
-// accumulator epilogues.
+// The qkv bias gradient is taken in the accumulator epilogues: the Q third by one warp reduction per item, the V
+// third from an all-ones row of P^T (sum_k dV = sum_q dO), the K third is identically zero.
 constexpr int kBwdThreads = (kSoftmaxWarps + 1) * 32;
 constexpr int kRing = 4;                   // dS^T tiles (64 queries each): two pairs in flight
 
 struct BwdMaps {
-  CUtensorMap qkv_a, qkv_b, do_a, do_b, o_a, o_b;   // box rows RA / RB
+  CUtensorMap qkv_a, qkv_b, do_a, do_b;      // box rows RA / RB
 };
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -397,12 +394,6 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_items, int N, int H,
                    float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
-#ifdef FC_ATTN_PROF
-  __shared__ long long prof_s[16 * 12];
-#define BPROF(slot) do { if (threadIdx.x == 0 && cc < 16) prof_s[cc * 12 + (slot)] = clock64(); } while (0)
-#else
-#define BPROF(slot) do { } while (0)
-#endif
   if (smem_u32(smem) & 1023) __trap();
   const int RA = N > 128 ? 128 : ((N + 15) & ~15);
   const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
@@ -410,11 +401,11 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
   const int nkt = RB ? 2 : 1;                 // key tiles
   const int nqc = (NK + 63) >> 6;             // query chunks per key tile
   const int op_bytes = NK * 128;
-  // smem: Q | K | V | dO | O | dS^T ring | lse2, D vectors [2][256] | barriers
-  const uint32_t sQ = smem_u32(smem), sK = sQ + op_bytes, sV = sK + op_bytes, sDO = sV + op_bytes, sO = sDO + op_bytes;
-  const uint32_t sRing = sO + op_bytes;
-  uint8_t* vec_base = smem + 5 * op_bytes + kRing * TILE;
-  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(vec_base + 2048);
+  // smem: Q | K | V | dO | dS^T ring | lse2,D vectors [2 items][2][256] | barriers
+  const uint32_t sQ = smem_u32(smem), sK = sQ + op_bytes, sV = sK + op_bytes, sDO = sV + op_bytes;
+  const uint32_t sRing = sDO + op_bytes;
+  uint8_t* vec_base = smem + 4 * op_bytes + kRing * TILE;
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(vec_base + 4096);
   uint64_t* sdp_full = tma_bar + 1;           // [2] S^T/dP^T chunk buffer written
   uint64_t* e_done = sdp_full + 2;            // [2] chunk consumed: P^T in TMEM, dS^T in smem          (16 arrivals)
   uint64_t* pair_done = e_done + 2;           // [2] dK/dQ (and every earlier MMA) of a pair completed
@@ -460,17 +451,15 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
       prefetch_tmap(&maps.qkv_b);
       prefetch_tmap(&maps.do_a);
       prefetch_tmap(&maps.do_b);
-      prefetch_tmap(&maps.o_a);
-      prefetch_tmap(&maps.o_b);
       const uint32_t idesc_dv = umma_idesc_bf16(128, HD, 0, 1);    // A K-major (TMEM / dS^T tile), B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // A = dS^T tile read MN-major, B MN-major
       auto load_item = [&](int item, bool prefetch_only) {
         int b, h;
         item_bh(item, b, h);
-        if (!prefetch_only) mbar_arrive_expect_tx(tma_bar, 5 * op_bytes);
-        for (int op = 0; op < 5; ++op) {      // Q, K, V (columns of qkv), dO, O
-          const CUtensorMap* ma = op < 3 ? &maps.qkv_a : (op == 3 ? &maps.do_a : &maps.o_a);
-          const CUtensorMap* mb = op < 3 ? &maps.qkv_b : (op == 3 ? &maps.do_b : &maps.o_b);
+        if (!prefetch_only) mbar_arrive_expect_tx(tma_bar, 4 * op_bytes);
+        for (int op = 0; op < 4; ++op) {      // Q, K, V (columns of qkv), dO
+          const CUtensorMap* ma = op < 3 ? &maps.qkv_a : &maps.do_a;
+          const CUtensorMap* mb = op < 3 ? &maps.qkv_b : &maps.do_b;
           const int col = (op < 3 ? op * d : 0) + h * HD;
           if (prefetch_only) {
             tma_prefetch_3d(ma, col, 0, b);
@@ -518,7 +507,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
             for (int j = 0; j < (W >> 4); ++j, b += 128) umma_bf16_ts(tDV, tb + 16 * j, b, idesc_dv, (qc | j) != 0);
           }
           // the chunk two ahead reuses this chunk's buffer: ordered behind dV above in the MMA pipe, and issued
-          // before the pair's dK/dQ so the elementwise warps never wait for it
+          // before the pair's dK/dQ so the elementwise warps do not wait for it
           if (lc + 2 < chunks) issue_sdp(lc + 2, cc + 2);
           if ((qc & 1) || qc == nqc - 1) {    // a pair of chunks (<= 128 queries) is complete
             const int qt = qc >> 1, q0 = qt * 128;
@@ -551,26 +540,21 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t vec = smem_u32(vec_base);
     const float sc = scale * 1.4426950408889634f;
-    // lse2[q] = lse*log2(e) and D[q] = <dO[q], O[q]> of the item whose operands just landed: one token per thread
-    // (<= 256 of the 512), dO and O rows read from the swizzled smem tiles (the same physical 16-byte chunk of both
-    // rows holds the same logical columns); rows >= N are TMA zero fill -> D = 0, and get lse2 = +inf -> P = 0.
-    auto lse_of = [&](int k) -> float {
-      const int t = threadIdx.x;
-      if (t >= N || k >= n_my) return INFINITY;
-      int b, h;
-      item_bh(first + k * stride, b, h);
-      return lse_g[(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
-    };
-    auto compute_vectors = [&](float l2) {
+    // lse2 / D of an item -> vector buffer (item parity); one token per thread (<= 256 < 512 threads)
+    auto compute_vectors = [&](int k) {
       const int t = threadIdx.x;
       if (t < 256) {
-        float dd = 0.f;
-        if (t < NK) {
+        int b, h;
+        item_bh(first + k * stride, b, h);
+        float l2 = INFINITY, dd = 0.f;        // padding queries: P = exp2(-inf) = 0
+        if (t < N) {
+          l2 = lse_g[(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
+          const uint4* po = reinterpret_cast<const uint4*>(o_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
+          const uint4* pg = reinterpret_cast<const uint4*>(do_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint32_t aw[4], gw[4];
-            lds_u4(sO + t * 128 + i * 16, aw);
-            lds_u4(sDO + t * 128 + i * 16, gw);
+            const uint4 a = po[i], g = pg[i];
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               dd = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), dd);
@@ -578,14 +562,13 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
             }
           }
         }
-        st_shared_f32(vec + t * 4, l2);
-        st_shared_f32(vec + 1024 + t * 4, dd);
+        st_shared_f32(vec + (k & 1) * 2048 + t * 4, l2);
+        st_shared_f32(vec + (k & 1) * 2048 + 1024 + t * 4, dd);
       }
     };
     // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv.
-    // colsum (nullable): += the column sums of what was stored (the qkv bias gradient), reduced over the warp's
-    // 32 rows by a halving butterfly (16 shuffles for 16 columns) and one atomic per column and warp.
-    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col, float* colsum) {
+    // The rounded values that were stored are returned in v (0 for rows past the sequence) for the bias gradient.
+    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col, float (&v)[16], bool accumulate_v) {
       float f[16];
       tmem_ld_32x16(tcol + lane_off + grp * 16, f);
       tmem_ld_wait();
@@ -597,27 +580,35 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
-      if (colsum != nullptr) {
-        float v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {         // the stored (rounded) values; rows past the sequence count as 0
-          v[2 * i] = tok < N ? __uint_as_float(pk[i] << 16) : 0.f;
-          v[2 * i + 1] = tok < N ? __uint_as_float(pk[i] & 0xFFFF0000u) : 0.f;
-        }
-#pragma unroll
-        for (int w = 8; w >= 1; w >>= 1) {    // lane-mask 16, 8, 4, 2: keep one half of the columns, add the partner's
-          const bool hi = (lane & (2 * w)) != 0;
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            const float send = hi ? v[j] : v[j + w];
-            const float keep = hi ? v[j + w] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
-          }
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        if ((lane & 1) == 0) atomicAdd(colsum + col + grp * 16 + (lane >> 1), v[0]);
+      for (int i = 0; i < 8; ++i) {
+        const float lo = tok < N ? __uint_as_float(pk[i] << 16) : 0.f, hi = tok < N ? __uint_as_float(pk[i] & 0xFFFF0000u) : 0.f;
+        v[2 * i] = accumulate_v ? v[2 * i] + lo : lo;
+        v[2 * i + 1] = accumulate_v ? v[2 * i + 1] + hi : hi;
       }
     };
+    // colsum[col + 16*grp + c] += sum over the warp's 32 rows of v[c]: halving butterfly (16 shuffles for the 16
+    // columns) and one atomic per column and warp.
+    auto add_colsum = [&](float (&v)[16], float* colsum, int col) {
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1) {      // lane-mask 16, 8, 4, 2: keep one half of the columns, add the partner's
+        const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+          const float send = hi ? v[j] : v[j + w];
+          const float keep = hi ? v[j + w] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+        }
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      if ((lane & 1) == 0) atomicAdd(colsum + col + grp * 16 + (lane >> 1), v[0]);
+    };
+    // V bias gradient without a reduction: sum_k dV[k,:] = sum_q (sum_k P[q,k]) dO[q,:] = sum_q dO[q,:].  When the
+    // last key tile has a spare row (N % 128 != 0) its row 127 of P^T is set to 1 for every real query, so that
+    // row of the dV accumulator IS the column sum (fp32, exact) and its 4 threads add it to dbias.
+    const bool ones_row = dbias != nullptr && (N & 127) != 0;
+    if (n_my > 0) compute_vectors(0);
+    softmax_warps_sync();
     int cc = 0, pair = 0;
     int pend_kv = -1, pend_kv_pair = 0, pend_kv_item = 0;   // key tile whose dV/dK still sit in TMEM (-1: none)
     int pend_dq_item = -1, pend_dq_pair = 0;                // item whose dQ still sits in TMEM
@@ -628,9 +619,20 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         int b, h;
         item_bh(pend_kv_item, b, h);
         const int key = pend_kv * 128 + row;
-        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD, dbias);
+        float v[16];
+        if (ones_row && pend_kv == nkt - 1 && quarter == 3) {    // warp-uniform: tcgen05.ld is a whole-warp instruction
+          float f[16];
+          tmem_ld_32x16(tDV + lane_off + grp * 16, f);
+          tmem_ld_wait();
+          if (lane == 31) {                   // row 127, the all-ones row: sum_q dO[q, 16*grp .. +16)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) atomicAdd(dbias + 2 * d + h * HD + grp * 16 + c, f[c]);
+          }
+        }
+        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD, v, false);
+        if (dbias != nullptr && !ones_row) add_colsum(v, dbias, 2 * d + h * HD);
         // the K bias gradient is identically zero (softmax is invariant to a shift of the scores): nothing to add
-        store_acc(tDK, scale, key, b, d + h * HD, nullptr);
+        store_acc(tDK, scale, key, b, d + h * HD, v, false);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
@@ -641,44 +643,31 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
         tc_fence_after();
         int b, h;
         item_bh(pend_dq_item, b, h);
-        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, dbias);
+        float v[16];                          // both query tiles summed per thread: one reduction per item
+        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, v, qt > 0);
+        if (dbias != nullptr) add_colsum(v, dbias, h * HD);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_free);
         pend_dq_item = -1;
       }
     };
-    // The accumulators of a finished key tile are read out (flush_pending) as late as the protocol allows — after
-    // the second chunk of the next tile (the control warp cannot issue that tile's third S^T/dP^T before it has
-    // the accumulators back): by then the ~25 MMAs queued behind the tile's last chunk have drained, and a
-    // tcgen05.ld issued earlier would sit behind them.  At an item boundary the read-out runs under the TMA loads
-    // of the next item.
-    float l2_next = lse_of(0);
-    const uint32_t vl = vec, vd = vec + 1024;
     for (int k = 0; k < n_my; ++k) {
       const int item = first + k * stride;
-      if (k > 0) flush_pending();             // previous item's dV/dK/dQ, under the TMA loads of this one
-      mbar_wait(tma_bar, k & 1);              // this item's operands (dO and O for the vectors) have landed
-      compute_vectors(l2_next);
-      l2_next = lse_of(k + 1);                // a 2-us global load: issued one item ahead of its use
-      softmax_warps_sync();                   // vectors visible to every warp
+      const uint32_t vl = vec + (k & 1) * 2048, vd = vl + 1024;
       for (int kt = 0; kt < nkt; ++kt) {
         for (int qc = 0; qc < nqc; ++qc, ++cc) {
           const int W = min(64, NK - 64 * qc);
           const uint32_t tb = tmem + (cc & 1) * 128 + lane_off;
-          BPROF(0);
           // ring tile of this chunk; its previous user (pair - 2) must have been consumed by dK/dQ
           if ((qc & 1) == 0 && pair >= 2) mbar_wait(&pair_done[pair & 1], ((pair >> 1) - 1) & 1);
-          BPROF(1);
           mbar_wait(&sdp_full[cc & 1], (cc >> 1) & 1);
           tc_fence_after();
-          BPROF(2);
           if (16 * grp < W) {                 // warp-uniform
             float s[16], dp[16];
             tmem_ld_32x16(tb + 16 * grp, s);
             tmem_ld_32x16(tb + 64 + 16 * grp, dp);
             tmem_ld_wait();
-            BPROF(3);
             const int q0 = 64 * qc + 16 * grp;
             uint32_t pp[8], ds[8];
 #pragma unroll
@@ -692,6 +681,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
                 p[e] = ex2(fmaf(s[i + e], sc, -l[e]));
                 g[e] = p[e] * (dp[i + e] - dv[e]);
               }
+              if (ones_row && row == 127 && kt == nkt - 1) {     // see ones_row: P^T[127, q] = [q < N]
+#pragma unroll
+                for (int e = 0; e < 4; ++e) p[e] = q0 + i + e < N ? 1.0f : 0.0f;
+              }
               pp[i >> 1] = pack2(p[0], p[1]);
               pp[(i >> 1) + 1] = pack2(p[2], p[3]);
               ds[i >> 1] = pack2(g[0], g[1]);
@@ -702,16 +695,13 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
             const uint32_t rsw = (tile + row * 128) | ((row & 7) << 4);
             sts_u4(rsw ^ ((2 * grp) << 4), ds[0], ds[1], ds[2], ds[3]);
             sts_u4(rsw ^ ((2 * grp + 1) << 4), ds[4], ds[5], ds[6], ds[7]);
-            BPROF(4);
             tmem_st_wait();
             fence_proxy_async();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&e_done[cc & 1]);
-          BPROF(5);
-          if (qc == (nqc > 1 ? 1 : 0)) flush_pending();   // latest point for the previous key tile's dV/dK (see above)
-          BPROF(6);
+          flush_pending();                    // outputs of the previous key tile / item, now that this chunk is handed over
           if ((qc & 1) || qc == nqc - 1) {
             if (qc == nqc - 1) {
               pend_kv = kt;
@@ -724,18 +714,17 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
             }
             ++pair;
           }
-          BPROF(7);
+          if (kt == 0 && qc == 0 && k + 1 < n_my) {   // next item's vectors, one item ahead
+            compute_vectors(k + 1);
+          }
         }
       }
-      softmax_warps_sync();                   // every warp is done with this item's vectors
+      softmax_warps_sync();                   // next item's vectors are visible to every warp
     }
     flush_pending();
   }
   tc_fence_before();
   __syncthreads();
-#ifdef FC_ATTN_PROF
-  if (blockIdx.x == 0 && threadIdx.x < 16 * 12) g_attn_prof[threadIdx.x] = prof_s[threadIdx.x];
-#endif
   if (warp == kSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -822,10 +811,8 @@ extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_
   if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
   if (!rc) rc = make_tmap3(&maps.do_a, d_out, B, N, H * HD, RA);
   if (!rc) rc = make_tmap3(&maps.do_b, d_out, B, N, H * HD, RB ? RB : RA);
-  if (!rc) rc = make_tmap3(&maps.o_a, out, B, N, H * HD, RA);
-  if (!rc) rc = make_tmap3(&maps.o_b, out, B, N, H * HD, RB ? RB : RA);
   if (rc) return rc;
-  const int smem = 5 * NK * 128 + kRing * TILE + 2048 + 128;
+  const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
   FC_SMEM_OPT_IN(attn_bwd_tc_kernel, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
   const int items = B * H;
   const int sms = fc_num_sms(device);

@@ -47,7 +47,8 @@ def test_attention_forward(B, N, H, cuda):
     _close(lse, ref_lse, 1e-4, 1e-3, "lse")
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 6), (2, 40, 1), (2, 200, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 6), (2, 40, 1), (2, 200, 2), (2, 128, 2), (1, 256, 1),
+                                   (3, 129, 2), (4, 7, 3)])
 def test_attention_backward(B, N, H, cuda):
     torch.manual_seed(1)
     qkv = torch.randn(B, N, 3, H, 64, device=cuda).to(torch.bfloat16)
@@ -55,18 +56,19 @@ def test_attention_backward(B, N, H, cuda):
     out, lse = ops.attention_fwd(qkv, B, N, H)
     dbias = torch.ones(3 * H * 64, device=cuda)
     dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, dbias=dbias)
-    # fused qkv bias gradient: += column sums of the stored dQ and dV; the K third is left untouched because it is
-    # identically zero (softmax is shift-invariant) — the fp32 autograd value below is ~1e-7
-    sums = dqkv.float().view(B * N, 3, H * 64).sum(0)
-    _close(dbias.view(3, -1)[0], 1.0 + sums[0], 1e-3, 2e-3, "fused q bias gradient")
-    _close(dbias.view(3, -1)[2], 1.0 + sums[2], 1e-3, 2e-3, "fused v bias gradient")
-    assert torch.equal(dbias.view(3, -1)[1], torch.ones(H * 64, device=cuda))
     x = qkv.float().requires_grad_(True)
     q, k, v = x.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
     o = (((q * 0.125) @ k.transpose(-2, -1)).softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * 64)
     o.backward(dout.float())
-    kb = x.grad.view(B * N, 3, H * 64).sum(0)[1]
-    assert kb.abs().max().item() < 1e-4 * x.grad.abs().max().item() * (B * N) ** 0.5, "reference K bias gradient is ~0"
+    # fused qkv bias gradient: dbias += column sums of dQ and dV (the V third is taken exactly, as the column sums of
+    # dO through an all-ones row of P^T); the K third is left untouched because it is identically zero (softmax
+    # is shift-invariant) — the fp32 autograd value is ~1e-7.  Bar: 2e-2 of the gradient's scale (bf16 mode).
+    gb = x.grad.view(B * N, 3, H * 64).sum(0)
+    assert gb[1].abs().max().item() < 1e-4 * x.grad.abs().max().item() * (B * N) ** 0.5, "reference K bias gradient is ~0"
+    got = dbias.view(3, -1) - 1.0
+    for third, name in ((0, "q"), (2, "v")):
+        _close(got[third], gb[third], 2e-2, 2e-2 * gb[third].abs().max().item(), f"fused {name} bias gradient")
+    assert torch.equal(dbias.view(3, -1)[1], torch.ones(H * 64, device=cuda))
     scale = x.grad.abs().max().item()
     _close(dqkv, x.grad, 3e-2, 1.5e-2 * scale, "dqkv")
     # aggregate error well inside the bf16 budget
