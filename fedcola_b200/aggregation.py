@@ -139,20 +139,62 @@ def upload_keys(spec: MatSpec, with_aux_flag: bool, modality: str):
     return out
 
 
+_PLAN_CACHE = {}          # structural signature -> symbolic tables (addresses as (owner, byte offset))
+_PLAN_CACHE_MAX = 64
+
+
 class AggregationPlan:
-    """Tables for one fc_aggregate launch (see include/fedcola_b200.h)."""
+    """Tables for one fc_aggregate launch (see include/fedcola_b200.h).
+
+    The tables depend on the sampled clients only through their (spec, dataset, modality, task, size) in id order,
+    so they are built symbolically — every address as (owner, byte offset) — memoised on that signature, and turned
+    into device addresses with a few vectorised numpy operations per round."""
 
     def __init__(self, globals_: List[GlobalCtx], clients: List[ClientCtx], param_scope: Dict[str, str],
                  args_modalities, share_scope_flag, compensation, with_aux, mode=LERP, fedavg=False,
                  include_global_term=True):
         clients = sorted(clients, key=lambda c: c.id)
         self.mode = mode
-        tile = int(_lib.lib().fc_aggregate_tile_floats())
-        coef_cache = {}
-        ukeys = {c.id: upload_keys(c.spec, with_aux, c.modality) for c in clients}
         if mode == LERP and any(c.arena is None for c in clients):
             raise ValueError("sequential-lerp aggregation needs every sampled client's arena on this GPU; "
                              "use mode=WSUM for clients sharded across ranks")
+        sig = (mode, bool(fedavg), bool(include_global_term), tuple(args_modalities), share_scope_flag,
+               bool(compensation), bool(with_aux), id(param_scope), len(param_scope),
+               tuple((g.spec.signature, g.dataset, g.modality, g.task, g.out_modality_scale) for g in globals_),
+               tuple((c.spec.signature, c.dataset, c.modality, c.task, c.size, c.arena is None) for c in clients))
+        sym = _PLAN_CACHE.get(sig)
+        if sym is None:
+            sym = self._build_symbolic(globals_, clients, param_scope, args_modalities, share_scope_flag, compensation,
+                                       with_aux, mode, fedavg, include_global_term)
+            sym["_pin"] = param_scope            # the key holds its id(): keep it alive
+            if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+                _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+            _PLAN_CACHE[sig] = sym
+        self.job_names = sym["job_names"]
+        self.algorithmic_bytes = sym["algorithmic_bytes"]
+        self.n_jobs, self.n_tiles = sym["n_jobs"], sym["n_tiles"]
+        # ---- addresses of this round's arenas ----
+        gin = np.asarray([g.arena_in.data_ptr() for g in globals_] + [0], dtype=np.uint64)
+        gout = np.asarray([g.arena_out.data_ptr() for g in globals_] + [0], dtype=np.uint64)
+        cbase = np.asarray([c.arena.data_ptr() if c.arena is not None else 0 for c in clients] + [0], dtype=np.uint64)
+        self.host = dict(
+            job_tile_start=sym["job_tile_start"], job_numel=sym["job_numel"], job_nout=sym["job_nout"],
+            job_gin=gin[sym["job_g"]] + sym["job_g_off"], job_gout=gout[sym["job_g"]] + sym["job_g_off"],
+            job_gscale=sym["job_gscale"], job_src_start=sym["job_src_start"],
+            src_ptr=cbase[sym["src_owner"]] + sym["src_off"], src_flag=sym["src_flag"],
+            scale_ptr=cbase[sym["scale_owner"]] + sym["scale_off"], coef=sym["coef"],
+        )
+        self.dev = None
+        self._keep = (globals_, clients)
+
+    @staticmethod
+    def _build_symbolic(globals_, clients, param_scope, args_modalities, share_scope_flag, compensation, with_aux,
+                        mode, fedavg, include_global_term):
+        tile = int(_lib.lib().fc_aggregate_tile_floats())
+        coef_cache = {}
+        ukeys = {c.id: upload_keys(c.spec, with_aux, c.modality) for c in clients}
+        pos = {c.id: i for i, c in enumerate(clients)}
+        NONE_G, NONE_C = len(globals_), len(clients)      # index of the all-zero sentinel address
 
         # union of output parameter names, in first-seen order
         names, outs = [], {}
@@ -164,10 +206,10 @@ class AggregationPlan:
                     names.append(kk)
                 outs[kk].append(gi)
 
-        job_numel, job_nout, job_gin, job_gout, job_gscale = [], [], [], [], []
-        job_src_start, src_ptr, src_flag, scale_ptr, coef = [0], [], [], [], []
-        self.job_names = []
-        self.algorithmic_bytes = 0
+        job_numel, job_nout, job_g, job_g_off, job_gscale = [], [], [], [], []
+        job_src_start, src_owner, src_off, src_flag, scale_owner, scale_off, coef = [0], [], [], [], [], [], []
+        job_names = []
+        algorithmic_bytes = 0
         for name, numel in names:
             glist = outs[(name, numel)]
             for g0 in range(0, len(glist), MAX_OUT):
@@ -210,51 +252,45 @@ class AggregationPlan:
                 else:
                     gsc = [np.float32(0)] * len(gs)
                 rows = [r for r in rows if r[0].arena is not None]     # remote clients only shape the weights
-                self.job_names.append(name)
+                job_names.append(name)
                 job_numel.append(numel)
                 job_nout.append(len(gs))
                 for o in range(MAX_OUT):
                     if o < len(gs):
-                        g = globals_[gs[o]]
-                        off = g.spec.seg(name).offset * 4
-                        job_gin.append(g.arena_in.data_ptr() + off)
-                        job_gout.append(g.arena_out.data_ptr() + off)
+                        job_g.append(gs[o]), job_g_off.append(globals_[gs[o]].spec.seg(name).offset * 4)
                         job_gscale.append(gsc[o])
                     else:
-                        job_gin.append(0), job_gout.append(0), job_gscale.append(np.float32(0))
+                        job_g.append(NONE_G), job_g_off.append(0), job_gscale.append(np.float32(0))
                 for c, off, aux, cvals in rows:
-                    base = c.arena.data_ptr()
                     cpad = cvals + [np.float32(0)] * (MAX_OUT - len(cvals))
                     if aux:      # upload() hands the server W + A*s: a HOLD entry (W) then a MERGE entry (A, s)
-                        src_ptr.append(base + off * 4), src_flag.append(SRC_HOLD), scale_ptr.append(0)
+                        src_owner.append(pos[c.id]), src_off.append(off * 4), src_flag.append(SRC_HOLD)
+                        scale_owner.append(NONE_C), scale_off.append(0)
                         coef.extend([np.float32(0)] * MAX_OUT)
-                        src_ptr.append(base + aux[0] * 4), src_flag.append(SRC_MERGE)
-                        scale_ptr.append(base + aux[1] * 4)
+                        src_owner.append(pos[c.id]), src_off.append(aux[0] * 4), src_flag.append(SRC_MERGE)
+                        scale_owner.append(pos[c.id]), scale_off.append(aux[1] * 4)
                         coef.extend(cpad)
                     else:
-                        src_ptr.append(base + off * 4), src_flag.append(SRC_PLAIN), scale_ptr.append(0)
+                        src_owner.append(pos[c.id]), src_off.append(off * 4), src_flag.append(SRC_PLAIN)
+                        scale_owner.append(NONE_C), scale_off.append(0)
                         coef.extend(cpad)
-                    self.algorithmic_bytes += 4 * numel * (2 if aux else 1)
-                job_src_start.append(len(src_ptr))
-                self.algorithmic_bytes += 4 * numel * 2 * len(gs)
+                    algorithmic_bytes += 4 * numel * (2 if aux else 1)
+                job_src_start.append(len(src_owner))
+                algorithmic_bytes += 4 * numel * 2 * len(gs)
         tiles = [(n + tile - 1) // tile for n in job_numel]
-        self.n_jobs = len(job_numel)
-        self.n_tiles = int(sum(tiles))
-        self.host = dict(
+        return dict(
+            job_names=job_names, algorithmic_bytes=algorithmic_bytes, n_jobs=len(job_numel), n_tiles=int(sum(tiles)),
             job_tile_start=np.concatenate([[0], np.cumsum(tiles)]).astype(np.int32),
             job_numel=np.asarray(job_numel, dtype=np.int64),
             job_nout=np.asarray(job_nout, dtype=np.int32),
-            job_gin=np.asarray(job_gin, dtype=np.uint64),
-            job_gout=np.asarray(job_gout, dtype=np.uint64),
+            job_g=np.asarray(job_g, dtype=np.int64), job_g_off=np.asarray(job_g_off, dtype=np.uint64),
             job_gscale=np.asarray(job_gscale, dtype=np.float32),
             job_src_start=np.asarray(job_src_start, dtype=np.int32),
-            src_ptr=np.asarray(src_ptr, dtype=np.uint64),
+            src_owner=np.asarray(src_owner, dtype=np.int64), src_off=np.asarray(src_off, dtype=np.uint64),
             src_flag=np.asarray(src_flag, dtype=np.int32),
-            scale_ptr=np.asarray(scale_ptr, dtype=np.uint64),
+            scale_owner=np.asarray(scale_owner, dtype=np.int64), scale_off=np.asarray(scale_off, dtype=np.uint64),
             coef=np.asarray(coef, dtype=np.float32).reshape(-1),
         )
-        self.dev = None
-        self._keep = (globals_, clients)
 
     def to_device(self, device):
         """Pack all tables into ONE pinned host buffer and copy once."""

@@ -79,6 +79,14 @@ class MatSpec:
 
     # ---- derived -------------------------------------------------------------------------------
     @property
+    def signature(self):
+        """Hashable identity of the layout: equal for deep copies (the segment table is a pure function of it)."""
+        return (self.embed_dim, self.depth, self.num_heads, self.modalities, self.num_classes, self.tasks,
+                self.vocab_size, self.max_text_len, self.img_size, self.patch_size, self.in_chans, self.mlp_ratio,
+                self.with_aux, self.aux_trained, self.aux_attn_only, self.aux_mlp_only, self.share_scope,
+                self.shared_param, self.colearn_param, self.total)
+
+    @property
     def head_dim(self):
         return self.embed_dim // self.num_heads
 

@@ -152,3 +152,43 @@ def test_oracle_and_plan_match_reference_golden(case):
             assert sha(got[k]) == h, ("plan", case, g.dataset, k)
             if k in expect[g.dataset]:
                 assert sha(expect[g.dataset][k]) == h, ("oracle", case, g.dataset, k)
+
+
+def test_memoised_plan_is_rebound_to_new_arenas():
+    """The symbolic tables are cached on the structural signature of the round; a hit must address THIS round's
+    arenas (fresh allocations, fresh values, deep-copied specs) and a different size pattern must miss."""
+    import copy
+    from helpers import run_plan_numpy
+    case = "fedcola_attn_modality_comp_aux"
+    gl, cl, scope, flags = build_agg_case(case)
+    agg._PLAN_CACHE.clear()
+    agg.AggregationPlan(gl, cl, scope, mode=agg.LERP, **flags)
+    assert len(agg._PLAN_CACHE) == 1
+    rng = np.random.default_rng(7)
+    gl2 = [agg.GlobalCtx(g.dataset, g.modality, g.task, g.out_modality_scale, copy.deepcopy(g.spec),
+                         torch.from_numpy(rng.standard_normal(g.spec.total).astype(np.float32)), torch.empty(g.spec.total))
+           for g in gl]
+    for g in gl2:
+        g.arena_out.copy_(g.arena_in)
+    cl2 = [agg.ClientCtx(c.id + 100, c.dataset, c.modality, c.task, c.size, copy.deepcopy(c.spec),
+                         torch.from_numpy(rng.standard_normal(c.spec.total).astype(np.float32))) for c in cl]
+    plan = agg.AggregationPlan(gl2, cl2, scope, mode=agg.LERP, **flags)
+    assert len(agg._PLAN_CACHE) == 1, "same structure: cache hit"
+    run_plan_numpy(plan)
+    expect = oracle_aggregate(gl2, cl2, scope, flags)
+    for g in gl2:
+        got = state_dict_of(g.spec, g.arena_out.numpy())
+        for k, v in expect[g.dataset].items():
+            assert np.array_equal(got[k], v), (g.dataset, k)
+    cl3 = [agg.ClientCtx(c.id, c.dataset, c.modality, c.task, c.size + (1 if i == 0 else 0), c.spec, c.arena)
+           for i, c in enumerate(cl2)]
+    for g in gl2:
+        g.arena_out.copy_(g.arena_in)
+    plan3 = agg.AggregationPlan(gl2, cl3, scope, mode=agg.LERP, **flags)
+    assert len(agg._PLAN_CACHE) == 2, "different client sizes: new coefficients, new entry"
+    run_plan_numpy(plan3)
+    expect3 = oracle_aggregate(gl2, cl3, scope, flags)
+    for g in gl2:
+        got = state_dict_of(g.spec, g.arena_out.numpy())
+        for k, v in expect3[g.dataset].items():
+            assert np.array_equal(got[k], v), (g.dataset, k)
