@@ -341,7 +341,9 @@ class FedavgServer(BaseServer):
             client.trainer = None
 
     def _refresh_aux(self):
-        """aux_weight of every uni-modal global <- the other modality's global block weights (:821-845)."""
+        """aux_weight of every uni-modal global <- the other modality's global block weights (:821-845).
+        The (destination, source) views are resolved once per arena pair and copied with one multi-tensor call."""
+        cache = self.__dict__.setdefault("_aux_views", {})
         for dataset, model in self.global_models.items():
             modality = DATASET_2_MODALITY[dataset]
             if modality == "img+txt":
@@ -349,11 +351,19 @@ class FedavgServer(BaseServer):
             other_mod, a, b = ("txt", "blockses.0", "blockses.1") if modality == "img" else ("img", "blockses.1", "blockses.0")
             other = [d for d in self.global_models if DATASET_2_MODALITY[d] == other_mod][0]
             src = self.global_models[other]
-            with torch.no_grad():
+            key = (dataset, model.arena.data_ptr(), src.arena.data_ptr())
+            if key not in cache:
+                dsts, srcs = [], []
                 for k in model.spec.aux_keys():
                     s = model.spec.seg(k)
                     o = src.spec.seg(k.replace("aux_", "").replace(a, b))
-                    model.arena[s.offset:s.offset + s.numel].copy_(src.arena[o.offset:o.offset + o.numel])
+                    dsts.append(model.arena[s.offset:s.offset + s.numel])
+                    srcs.append(src.arena[o.offset:o.offset + o.numel])
+                cache[key] = (dsts, srcs)
+            dsts, srcs = cache[key]
+            if dsts:
+                with torch.no_grad():
+                    torch._foreach_copy_(dsts, srcs)
 
     # ---- the round (:784-856) ------------------------------------------------------------------------------
     def update(self):
