@@ -375,6 +375,21 @@ def main():
     ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     a = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything libraries print while running (NCCL's version
+    # banner, warnings) is routed to stderr at file-descriptor level, and fd 1 is handed back for the final print.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_print = print
+
+    def emit(*args, **kw):
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        real_print(*args, **kw)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
+    globals()["print"] = emit            # run_ours / run_reference print only their JSON line
     if a.impl == "reference":
         run_reference(a)
     else:
