@@ -25,9 +25,9 @@ def test_aggregation_golden_is_fresh():
 
 
 def test_mirror_init_and_keys_match_reference():
-    import timm
     from oracle import ref_shim
     ref_shim.install()
+    import timm
     from fedcola_b200.harness import make_args
     from fedcola_b200.models import mome as our
     for scope in ("modality", "all"):
@@ -47,3 +47,34 @@ def test_mirror_init_and_keys_match_reference():
                 assert [(k, p.requires_grad) for k, p in ref.named_parameters()] == \
                        [(k, p.requires_grad) for k, p in mine.named_parameters()]
                 assert list(ref.required_params().keys()) == list(mine.required_params().keys())
+
+
+def test_saved_state_dict_round_trips_through_the_reference(tmp_path):
+    """the `.pt` files finalize() writes (fedavgserver.py:888-894) carry the reference's key names and
+    shapes — a checkpoint written by this package loads strictly into the unmodified reference model and back."""
+    from oracle import ref_shim
+    ref_shim.install()
+    import timm
+    from fedcola_b200.harness import make_args
+    from fedcola_b200.models import mome as our
+    for mods, ncls, tasks, aux in ((["img", None], [100, None], ["cls", None], True),
+                                   ([None, "txt"], [None, 4], [None, "cls"], True),
+                                   (["img", "txt"], [None, None], ["rtv", "rtv"], False)):
+        args = make_args(shared_param="attn", share_scope="modality", vocab_size=512, seq_len=16)
+        kw = dict(pretrained=False, num_classes=ncls, modalities=mods, args=args, tasks=tasks, with_aux=aux,
+                  aux_trained=True, aux_attn_only=False, aux_mlp_only=False)
+        torch.manual_seed(11)
+        mine = our.create_model("mome_d64_l2", **kw)
+        with torch.no_grad():
+            mine._arena.add_(torch.randn_like(mine._arena) * 0.01)      # "trained" weights
+        path = os.path.join(tmp_path, "CIFAR100.pt")
+        torch.save({k: v.detach().cpu() for k, v in mine.state_dict().items()}, path)   # what finalize() does
+        torch.manual_seed(12)
+        ref = timm.create_model("mome_d64_l2", **kw)
+        missing, unexpected = ref.load_state_dict(torch.load(path), strict=True)
+        assert not missing and not unexpected
+        torch.manual_seed(13)
+        back = our.create_model("mome_d64_l2", **kw)
+        back.load_state_dict(ref.state_dict(), strict=True)
+        a, b = mine.state_dict(), back.state_dict()          # (the arenas differ in their alignment padding only)
+        assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
