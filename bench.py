@@ -120,6 +120,17 @@ def _log(msg):
 PREWARM_THREADED = 3
 
 
+def _agg_traffic():
+    """DRAM bytes (read + write) of the round's aggregation launch from the committed ncu capture, or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_aggregate_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _gemm_traffic():
     """DRAM bytes per GEMM launch from the committed ncu capture (profiles/r1_gemm_traffic.json), or (None, why)."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")
@@ -284,7 +295,8 @@ def run_ours(a):
             "train_phase_samples_per_s": round(samples / a.steps / (phases["local_training"] * 1e-3), 2),
             "aggregation": {"gbs": round(agg_best, 1), "frac_of_measured_hbm": round(agg_best / pk["hbm"], 4),
                             "bytes_per_round": int(agg_bytes[0]) if agg_bytes else 0,
-                            "ms": round(sorted(agg_ms)[len(agg_ms) // 2], 4) if agg_ms else None},
+                            "ms": round(sorted(agg_ms)[len(agg_ms) // 2], 4) if agg_ms else None,
+                            "traffic": _agg_traffic()},
         }
         if a.cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
