@@ -124,6 +124,24 @@ AGG_CASES = {
 ARGS_MODALITIES = {"CIFAR100": "img", "AG_NEWS": "txt", "Flickr30k": "img+txt"}
 
 
+def random_agg_case(seed):
+    """A seeded random aggregation configuration in AGG_CASES format (valid flag combinations only: compensation
+    needs share_scope in {all, modality, modality_exact}, fedavgserver.py:640-651)."""
+    import random
+    r = random.Random(seed)
+    sp = r.choice(["none", "attn", "blocks", "mlp"])
+    sc = r.choice(["dataset", "modality", "modality_exact", "all"])
+    comp = sc != "dataset" and r.random() < 0.5
+    aux = sp == "attn" and sc == "modality" and r.random() < 0.85
+    scales = [r.choice([1, 1, 0.5, 2]) for _ in range(3)]
+    datasets = ["CIFAR100", "AG_NEWS", "Flickr30k"]
+    clients = [(r.choice(datasets), r.randint(1, 40)) for _ in range(r.randint(1, 6))]
+    if r.random() < 0.7:                     # most rounds see every modality
+        clients += [(d, r.randint(1, 40)) for d in datasets if d not in {c[0] for c in clients}]
+    clients.sort(key=lambda c: datasets.index(c[0]))          # ids are grouped by dataset in the reference
+    return sp, sc, comp, aux, scales, datasets, clients
+
+
 def build_agg_case(name, device="cpu", seq_len=16):
     """Returns (globals: [GlobalCtx], clients: [ClientCtx], param_scope, flags dict)."""
     sp, sc, comp, aux, scales, datasets, clients = AGG_CASES[name]

@@ -192,3 +192,29 @@ def test_memoised_plan_is_rebound_to_new_arenas():
         got = state_dict_of(g.spec, g.arena_out.numpy())
         for k, v in expect3[g.dataset].items():
             assert np.array_equal(got[k], v), (g.dataset, k)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_configurations_match_oracle_bit_exact(seed):
+    """Seeded random scope / compensation / aux / scaling / client mixes: planner tables (executed like the kernel)
+    equal the oracle's sequential lerp bit for bit; the closed form agrees to 1e-6."""
+    from helpers import AGG_CASES, random_agg_case, run_plan_numpy
+    name = f"random_{seed}"
+    AGG_CASES[name] = random_agg_case(seed)
+    try:
+        gl, cl, scope, flags = build_agg_case(name)
+        expect = oracle_aggregate(gl, cl, scope, flags)
+        run_plan_numpy(agg.AggregationPlan(gl, cl, scope, mode=agg.LERP, **flags))
+        for g in gl:
+            got = state_dict_of(g.spec, g.arena_out.numpy())
+            for k, v in expect[g.dataset].items():
+                assert np.array_equal(got[k], v), (AGG_CASES[name], g.dataset, k)
+        for g in gl:
+            g.arena_out.copy_(g.arena_in)
+        run_plan_numpy(agg.AggregationPlan(gl, cl, scope, mode=agg.WSUM, **flags))
+        for g in gl:
+            got = state_dict_of(g.spec, g.arena_out.numpy())
+            for k, v in expect[g.dataset].items():
+                np.testing.assert_allclose(got[k], v, rtol=1e-6, atol=1e-7, err_msg=f"{AGG_CASES[name]} {g.dataset} {k}")
+    finally:
+        del AGG_CASES[name]

@@ -78,3 +78,25 @@ def test_saved_state_dict_round_trips_through_the_reference(tmp_path):
         back.load_state_dict(ref.state_dict(), strict=True)
         a, b = mine.state_dict(), back.state_dict()          # (the arenas differ in their alignment padding only)
         assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("seed", [0, 3, 4, 7, 9, 16, 21, 26, 33, 39])
+def test_random_configuration_against_the_live_reference(seed):
+    """Seeded random aggregation configurations (tests/helpers.random_agg_case) through the UNMODIFIED
+    FedavgServer._aggregate and through the planner tables: bit-identical new globals."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import make_golden
+    from fedcola_b200 import aggregation as agg
+    import helpers as H
+    name = f"random_{seed}"
+    H.AGG_CASES[name] = H.random_agg_case(seed)
+    try:
+        ref = make_golden.reference_aggregate(name)
+        gl, cl, scope, flags = H.build_agg_case(name)
+        H.run_plan_numpy(agg.AggregationPlan(gl, cl, scope, mode=agg.LERP, **flags))
+        for g in gl:
+            got = H.state_dict_of(g.spec, g.arena_out.numpy())
+            for k in g.spec.required_keys():
+                assert np.array_equal(got[k], ref[g.dataset][k]), (H.AGG_CASES[name], g.dataset, k)
+    finally:
+        del H.AGG_CASES[name]
