@@ -230,6 +230,14 @@ ROUND_CASES = {
     "fediot": (dict(algorithm="fedavg", shared_param="blocks", share_scope="modality_exact"),
                [("CIFAR100", 8, 51), ("CIFAR100", 4, 54), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)],
                ["CIFAR100", "AG_NEWS", "Flickr30k"]),
+    # share_scope=all: the txt encoder's attention aliases the img encoder's inside every model (mome.py:826-835)
+    "attn_all": (dict(algorithm="fedavg", shared_param="attn", share_scope="all"),
+                 [("CIFAR100", 8, 51), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)], ["CIFAR100", "AG_NEWS", "Flickr30k"]),
+    # the bench configuration's optimizer path: AdamW + gradient clipping, FedCola flags, two local epochs
+    "fedcola_adamw_clip": (dict(algorithm="fedavg", shared_param="attn", share_scope="modality", compensation=True,
+                                with_aux=True, aux_trained=True, optimizer="AdamW", lr=1e-3, max_grad_norm=1.0, E=2),
+                           [("CIFAR100", 8, 51), ("AG_NEWS", 12, 52), ("Flickr30k", 8, 53)],
+                           ["CIFAR100", "AG_NEWS", "Flickr30k"]),
 }
 
 
