@@ -100,3 +100,42 @@ def test_random_configuration_against_the_live_reference(seed):
                 assert np.array_equal(got[k], ref[g.dataset][k]), (H.AGG_CASES[name], g.dataset, k)
     finally:
         del H.AGG_CASES[name]
+
+
+def test_client_sampling_matches_the_live_reference():
+    """A11: FedavgServer._sample_clients (fedavgserver.py:282-312) — same ids AND same random-state consumption for
+    both sampling modes, the evaluation (exclude) branch and the warm-up modality filter."""
+    import random
+    from types import SimpleNamespace as NS
+    from oracle import ref_shim
+    ref_shim.install()
+    import src.server.fedavgserver as ref_fs
+    from fedcola_b200.server import fedavgserver as our_fs
+    datasets = ["CIFAR100", "AG_NEWS", "Flickr30k"]
+    mod = {"CIFAR100": "img", "AG_NEWS": "txt", "Flickr30k": "img+txt"}
+    rng = random.Random(5)
+    for trial in range(40):
+        per = [rng.randint(1, 9) for _ in datasets]
+        client_ds = [d for d, n in zip(datasets, per) for _ in range(n)]
+        K = len(client_ds)
+        args = NS(algorithm="fedavg", equal_sampled=rng.random() < 0.5, datasets=datasets, C=rng.choice([0.1, 0.25, 0.5, 1.0]),
+                  K=K, eval_fraction=rng.choice([0.3, 1.0]), warmup_modality=rng.choice(["none", "none", "img", "txt"]),
+                  warmup_rounds=2)
+        Cs = {d: rng.choice([0.2, 0.5, 1.0]) for d in datasets}
+        exclude = [] if args.equal_sampled or rng.random() < 0.6 else sorted(rng.sample(range(K), rng.randint(1, K)))
+        rnd = rng.choice([1, 2, 3])
+        seed = rng.randint(0, 10 ** 6)
+
+        def fake():
+            clients = [NS(id=i, dataset=d, modality=mod[d], device=None) for i, d in enumerate(client_ds)]
+            return NS(args=args, clients=clients, Cs=Cs, round=rnd, world_size=2, _client_device=lambda i: "cuda:0")
+
+        random.seed(seed)
+        want = ref_fs.FedavgServer._sample_clients(fake(), exclude=list(exclude))
+        state_ref = random.getstate()
+        random.seed(seed)
+        mine = fake()
+        got = our_fs.FedavgServer._sample_clients(mine, exclude=list(exclude))
+        assert got == want, (trial, vars(args), exclude)
+        assert random.getstate() == state_ref
+        assert mine._owner == {cid: i % 2 for i, cid in enumerate(got)}      # cuda:(i % ngpu) placement rule
