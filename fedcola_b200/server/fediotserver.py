@@ -1,8 +1,6 @@
 """`FediotServer`: `--algorithm fediot` is named by the reference's README/scripts but not shipped;
-it is FedavgServer with `--shared_param blocks --share_scope modality_exact`."""
+it is FedavgServer run with `--shared_param blocks --share_scope modality_exact`."""
 from .fedavgserver import FedavgServer
 
-
-class FediotServer(FedavgServer):
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
+FediotServer = type("FediotServer", (FedavgServer,),
+                    {"__module__": __name__, "__doc__": "FedAvg server under the FedIoT name (scope flags select the behaviour)."})

@@ -139,3 +139,29 @@ def test_client_sampling_matches_the_live_reference():
         assert got == want, (trial, vars(args), exclude)
         assert random.getstate() == state_ref
         assert mine._owner == {cid: i % 2 for i, cid in enumerate(got)}      # cuda:(i % ngpu) placement rule
+
+
+def test_dormant_server_optimizer_behaves_like_the_reference():
+    """`FedavgOptimizer.accumulate/step/zero_grad` (src/algorithm/fedavg.py, dormant upstream but name-resolved):
+    same tensors, bit for bit, as the unmodified class on a scripted sequence."""
+    import importlib
+    from oracle import ref_shim
+    ref_shim.install()
+    ref_cls = importlib.import_module("src.algorithm.fedavg").FedavgOptimizer
+    from fedcola_b200.algorithm.fedavg import FedavgOptimizer as our_cls
+
+    def run(cls):
+        torch.manual_seed(0)
+        sd = {f"w{i}": torch.nn.Parameter(torch.randn(5, 3)) for i in range(3)}
+        sd["bn.num_batches_tracked"] = torch.nn.Parameter(torch.zeros(1))
+        opt = cls(params=sd)
+        for k in range(3):
+            local = [(n, None if (n == "w1" and k == 1) else torch.randn_like(p)) for n, p in sd.items()]
+            opt.accumulate({"w0": 0.3, "w1": 0.5 * (k != 2), "w2": 0.2}, iter(local))
+        opt.step()
+        out = {n: p.detach().clone() for n, p in sd.items()}
+        opt.zero_grad()
+        return out, [float(p.grad.abs().sum()) for p in sd.values() if p.grad is not None]
+
+    a, b = run(ref_cls), run(our_cls)
+    assert all(torch.equal(a[0][k], b[0][k]) for k in a[0]) and a[1] == b[1]
