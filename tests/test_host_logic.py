@@ -1,0 +1,121 @@
+"""CPU: host-side tables the native driver consumes — arena layout, work-item (chunk) tables, operand/aux tables and
+the DropPath scale generator — checked for the invariants the kernels rely on."""
+import numpy as np
+import pytest
+import torch
+
+from fedcola_b200 import runtime
+from fedcola_b200.arena import MatSpec, BLOCK_ROLES
+from helpers import make_spec
+
+
+def specs():
+    out = []
+    for ds in ("CIFAR100", "AG_NEWS", "Flickr30k"):
+        for sp, sc, aux in (("none", "dataset", False), ("attn", "modality", True), ("attn", "all", False)):
+            out.append(make_spec(ds, sp, sc, with_aux=aux, aux_trained=aux))
+    return out
+
+
+@pytest.mark.parametrize("spec", specs(), ids=lambda s: f"{s.modalities}-{s.share_scope}-aux{int(s.with_aux)}")
+def test_arena_layout_invariants(spec):
+    """Every tensor starts on a 128-byte boundary, unique segments do not overlap and fill `total` (up to padding),
+    aliases (share_scope=all) point at an existing segment of the same shape."""
+    uniq = spec.unique_segments()
+    end = 0
+    for s in uniq:
+        assert s.offset % 32 == 0, s.key                     # 32 floats = 128 bytes
+        assert s.offset >= end, s.key
+        assert s.numel == int(np.prod(s.shape))
+        end = s.offset + s.numel
+    assert end <= spec.total and spec.total % 32 == 0
+    by_key = {s.key: s for s in spec.segments}
+    for s in spec.segments:
+        if s.alias_of is not None:
+            t = by_key[s.alias_of]
+            assert (s.offset, s.numel, s.shape) == (t.offset, t.numel, t.shape) and t.alias_of is None
+    assert spec.n_params() == sum(s.numel for s in uniq)
+    # required_params()/aux_params() partitions (mome.py:844-878)
+    req, aux = set(spec.required_keys()), set(spec.aux_keys())
+    if spec.with_aux and None in spec.modalities:
+        assert aux and not (req & aux)
+        assert all("aux" in k for k in aux)
+    assert all("cross_modal_scale" not in k for k in req) or not spec.with_aux
+
+
+@pytest.mark.parametrize("spec", specs()[:6], ids=lambda s: f"{s.modalities}-{s.share_scope}-aux{int(s.with_aux)}")
+def test_chunk_table_covers_trainable_elements_exactly_once(spec):
+    plan = runtime.ModelPlan(spec)
+    rg = {s.key: s.requires_grad for s in spec.segments}
+    table, nseg = plan.chunk_table(rg)
+    segs = [s for s in spec.unique_segments() if rg[s.key]]
+    assert nseg == len(segs)
+    cover = np.zeros(spec.total, dtype=np.int32)
+    for off, ln, seg in zip(table["off"], table["len"], table["seg"]):
+        assert 0 < ln <= plan.chunk and off % 4 == 0
+        s = segs[int(seg)]
+        assert s.offset <= off and off + ln <= s.offset + s.numel
+        cover[off:off + ln] += 1
+    want = np.zeros(spec.total, dtype=np.int32)
+    for s in segs:
+        want[s.offset:s.offset + s.numel] = 1
+    assert np.array_equal(cover, want)
+    assert plan.chunk_table(rg)[0] is table                                   # cached per signature
+    frozen = dict(rg)
+    frozen[segs[0].key] = False
+    t2, n2 = plan.chunk_table(frozen)
+    assert n2 == nseg - 1 and int(t2["len"].sum()) == int(table["len"].sum()) - segs[0].numel
+
+
+@pytest.mark.parametrize("spec", specs()[:6], ids=lambda s: f"{s.modalities}-{s.share_scope}-aux{int(s.with_aux)}")
+def test_operand_and_aux_tables(spec):
+    """One bf16 operand slot per Linear (64-element aligned, disjoint), aux entries exactly for the Linears that
+    carry (aux_weight, cross_modal_scale), block role offsets point into the arena."""
+    plan = runtime.ModelPlan(spec)
+    slots = sorted((int(r["dst_off"]), int(r["rows"]) * int(r["cols"])) for r in plan.prep_table)
+    end = 0
+    for dst, n in slots:
+        assert dst % 64 == 0 and dst >= end
+        end = dst + n
+    assert end <= plan.operand_elems
+    n_enc = sum(m is not None for m in spec.modalities)
+    n_lin = 4 * spec.depth * n_enc + (1 if spec.modalities[0] is not None else 0)      # + patch projection
+    assert len(plan.prep_table) == n_lin
+    expect_aux = 4 * spec.depth * n_enc if spec.has_aux else 0
+    assert len(plan.aux_table) == expect_aux
+    for e in range(2):
+        for j in range(spec.depth):
+            for k, role in enumerate(BLOCK_ROLES):
+                off = plan.desc.blk[e][j][k]
+                if spec.modalities[e] is None:
+                    assert off == -1
+                elif off >= 0:
+                    assert off < spec.total and off % 32 == 0, role
+
+
+def test_droppath_scales_follow_the_stochastic_depth_rule():
+    """timm DropPath as restated in oracle/ref_shim.py (parity unpinned: timm is not in the image): per block branch a
+    Bernoulli(keep) mask per sample divided by keep, keep = 1 - linspace(0, rate, depth)[j]; the 'reference' mode
+    consumes the generator exactly like the module sequence (encoder 0 first, attn branch then mlp branch)."""
+    spec = MatSpec(embed_dim=64, depth=4, num_heads=1, modalities=("img", "txt"), num_classes=(None, None),
+                   tasks=("rtv", "rtv"), vocab_size=64, max_text_len=8, drop_path_rate=0.3)
+    B = 16
+    assert runtime.droppath_scales(spec, B, "cpu", training=False) is None
+    torch.manual_seed(5)
+    got = runtime.droppath_scales(spec, B, "cpu", training=True, mode="reference")
+    torch.manual_seed(5)
+    dpr = [x.item() for x in torch.linspace(0, 0.3, 4)]
+    for e in range(2):
+        for j, r in enumerate(dpr):
+            for br in range(2):
+                if r <= 0:
+                    assert torch.all(got[e, j, br] == 1)
+                    continue
+                want = torch.empty(B, 1, 1).bernoulli_(1 - r).div_(1 - r).view(B)
+                assert torch.equal(got[e, j, br], want), (e, j, br)
+    fused = runtime.droppath_scales(spec, B, "cpu", training=True, mode="fused")
+    keep = torch.tensor([1 - r for r in dpr]).view(1, -1, 1, 1)
+    vals = fused * keep
+    assert torch.all((vals == 0) | ((vals - 1).abs() < 1e-6)) and torch.all(fused[:, 0] == 1)
+    zero = MatSpec(embed_dim=64, depth=2, num_heads=1, drop_path_rate=0.0)
+    assert runtime.droppath_scales(zero, B, "cpu", training=True) is None
