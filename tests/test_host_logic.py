@@ -119,3 +119,19 @@ def test_droppath_scales_follow_the_stochastic_depth_rule():
     assert torch.all((vals == 0) | ((vals - 1).abs() < 1e-6)) and torch.all(fused[:, 0] == 1)
     zero = MatSpec(embed_dim=64, depth=2, num_heads=1, drop_path_rate=0.0)
     assert runtime.droppath_scales(zero, B, "cpu", training=True) is None
+
+
+def test_attention_bias_gradient_identities():
+    """The identities the attention backward uses for the qkv bias gradient (csrc/attention.cu): with P = softmax(QK^T)
+    row-stochastic, sum_k dV[k] = sum_q dO[q] (an all-ones row of P^T yields it), and sum_k dK[k] = 0 exactly
+    (the scores are invariant to a shift of every key by the same vector)."""
+    torch.manual_seed(0)
+    B, H, N, D = 2, 3, 37, 64
+    q, k, v = (torch.randn(B, H, N, D, dtype=torch.float64, requires_grad=True) for _ in range(3))
+    do = torch.randn(B, H, N, D, dtype=torch.float64)
+    o = torch.softmax((q * D ** -0.5) @ k.transpose(-2, -1), dim=-1) @ v
+    o.backward(do)
+    assert torch.allclose(v.grad.sum(2), do.sum(2), rtol=1e-12, atol=1e-12)
+    assert k.grad.sum(2).abs().max() < 1e-12 * k.grad.abs().max() * N
+    # and the Q third is what the kernel reduces explicitly: nothing special about it
+    assert q.grad.sum(2).abs().max() > 1e-3
