@@ -786,7 +786,7 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
   const int items = B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
-  const int grid = (items + waves - 1) / waves;                  // balanced persistent grid (<= #SMs)
+  const int grid = fc_apply_grid_cap((items + waves - 1) / waves);   // balanced persistent grid (<= #SMs)
   const float scale_log2e = 0.125f * 1.4426950408889634f;        // 64^-0.5 * log2(e)
   attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       maps, static_cast<__nv_bfloat16*>(out), lse, items, N, H, nbuf, scale_log2e);
@@ -817,7 +817,7 @@ extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_
   const int items = B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
-  const int grid = (items + waves - 1) / waves;
+  const int grid = fc_apply_grid_cap((items + waves - 1) / waves);
   attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       maps, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(d_out), lse,
       static_cast<__nv_bfloat16*>(dqkv), dbias, items, N, H, 0.125f);

@@ -39,6 +39,14 @@ extern unsigned long long fc_launch_counter;
     if (!(cond)) FC_FAIL(FC_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// Test / measurement hook (fc_set_grid_cap): upper bound on the CTA count of the persistent kernels, so that parity
+// tests can force many tiles / items per CTA on small problems.  0 = no cap.
+extern int fc_grid_cap_value;
+static inline int fc_apply_grid_cap(int grid) {
+  const int cap = __atomic_load_n(&fc_grid_cap_value, __ATOMIC_RELAXED);
+  return (cap > 0 && grid > cap) ? cap : grid;
+}
+
 static inline int fc_num_sms(int device) {
   static thread_local int cached_dev = -1, cached = 0;
   if (cached_dev != device) {

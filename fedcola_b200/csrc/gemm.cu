@@ -686,6 +686,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = fc_num_sms(device);
   if (grid > total_tiles) grid = total_tiles;
+  grid = fc_apply_grid_cap(grid);
   ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K};
   const bool prof = __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) != 0;
   if (prof) {

@@ -1,12 +1,26 @@
 """Thin Python wrappers (ctypes) over the per-kernel C-ABI entry points — used by the parity tests and by
 code paths that need a single op.  The training hot loop does NOT go through here: it makes one native
 call per step (runtime.py -> csrc/mat_driver.cu)."""
+import contextlib
+
 import torch
 
 from . import _lib
 from ._lib import c_f, c_int, c_ll, c_vp, ptr
 
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_MULAUX, EPI_F32, EPI_ATOMIC_F32, EPI_PATCH = range(7)
+
+
+@contextlib.contextmanager
+def grid_cap(max_ctas):
+    """Cap the CTA count of the persistent kernels inside the block (fc_set_grid_cap): small problems then run
+    many tiles / items per CTA — the regime the bench shapes run in.  Process-wide (tests are single-threaded)."""
+    L = _lib.lib()
+    prev = L.fc_set_grid_cap(c_int(int(max_ctas)))
+    try:
+        yield
+    finally:
+        L.fc_set_grid_cap(c_int(prev))
 
 
 def _dev(t):

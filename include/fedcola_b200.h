@@ -25,6 +25,10 @@ const char* fc_last_error(void);
 int fc_abi_version(void);
 /* number of CUDA kernels this library has launched so far in this process */
 unsigned long long fc_launch_count(void);
+/* Test / measurement hook: cap the CTA count of the persistent kernels (fc_gemm_bf16, fc_attention_fwd/bwd) so that
+ * small problems run many tiles / items per CTA (the regime of the bench shapes).  0 = no cap.  Process-wide;
+ * returns the previous value. */
+int fc_set_grid_cap(int max_ctas);
 
 /* ------------------------------------------------------------------------------------------------
  * Server aggregation                                    ref: src/server/fedavgserver.py:597,656-666

@@ -130,11 +130,9 @@ def test_fused_client_steps_vs_reference_golden(kind, run, cuda):
     assert rel <= (0.35 if opt == "AdamW" else 2 * TOL), rel
 
 
-@pytest.mark.parametrize("kind,size,B", [("img", dict(embed_dim=192, depth=4, num_heads=3), 8),
-                                         ("txt", dict(embed_dim=192, depth=4, num_heads=3), 8),
-                                         ("pair", dict(embed_dim=128, depth=3, num_heads=2), 6)])
-def test_larger_models_vs_oracle(kind, size, B, cuda):
-    """BASELINE config-1 sized encoder (d=192, 4 blocks) against the fp32 oracle computed here on the CPU."""
+def _step_vs_oracle(kind, size, B, cuda, cap=0):
+    """One fused client step (forward + loss + backward, no optimizer) against the fp32 oracle computed here on the CPU."""
+    from fedcola_b200 import ops
     model, spec = build_model(kind, cuda, size=size)
     ds, _ = H.TRAIN_KINDS[kind]
     m = H.DS_MODALITY[ds]
@@ -149,14 +147,15 @@ def test_larger_models_vs_oracle(kind, size, B, cuda):
     ref_loss.backward()
     tr = R.ClientTrainer(model, optimizer="SGD", lr=0.0)
     tr.args.optimizer = R.OPT_NONE
-    if m == "img":
-        tr.step(a.to(cuda), None, b.to(cuda), R.LOSS_CE_IMG)
-    elif m == "txt":
-        tr.step(None, a.to(cuda), b.to(cuda), R.LOSS_CE_TXT)
-    else:
-        tr.step(a.to(cuda), b.to(cuda), None, R.LOSS_CONTRASTIVE)
-    torch.cuda.synchronize()
-    assert abs(tr.stats[0].item() - ref_loss.item()) <= TOL * abs(ref_loss.item())
+    with ops.grid_cap(cap):
+        if m == "img":
+            tr.step(a.to(cuda), None, b.to(cuda), R.LOSS_CE_IMG)
+        elif m == "txt":
+            tr.step(None, a.to(cuda), b.to(cuda), R.LOSS_CE_TXT)
+        else:
+            tr.step(a.to(cuda), b.to(cuda), None, R.LOSS_CONTRASTIVE)
+        torch.cuda.synchronize()
+    assert abs(tr.stats[0].item() - ref_loss.item()) <= TOL * abs(ref_loss.item()), (tr.stats[0].item(), ref_loss.item())
     grads = H.state_dict_of(spec, tr.grads.cpu().numpy())
     worst = {}
     for s in spec.unique_segments():
@@ -170,6 +169,30 @@ def test_larger_models_vs_oracle(kind, size, B, cuda):
     bad = {k: v for k, v in worst.items() if v > 2 * TOL}
     assert not bad, bad
     assert np.median(list(worst.values())) < TOL
+
+
+@pytest.mark.parametrize("kind,size,B", [("img", dict(embed_dim=192, depth=4, num_heads=3), 8),
+                                         ("txt", dict(embed_dim=192, depth=4, num_heads=3), 8),
+                                         ("pair", dict(embed_dim=128, depth=3, num_heads=2), 6)])
+def test_larger_models_vs_oracle(kind, size, B, cuda):
+    """BASELINE config-1 sized encoder (d=192, 4 blocks) against the fp32 oracle computed here on the CPU."""
+    _step_vs_oracle(kind, size, B, cuda)
+
+
+VIT_S = dict(embed_dim=384, depth=12, num_heads=6)
+VIT_B = dict(embed_dim=768, depth=12, num_heads=12)
+
+
+@pytest.mark.parametrize("kind,size,B,cap", [("img", VIT_S, 16, 0), ("img", VIT_S, 16, 37), ("pair", VIT_S, 12, 29),
+                                             ("txt_aux", VIT_S, 48, 11), ("img", VIT_B, 8, 0), ("img_aux", VIT_B, 6, 41),
+                                             ("txt", VIT_B, 32, 13)],
+                         ids=["vits-img-b16", "vits-img-b16-cap37", "vits-pair-b12-cap29", "vits-txt-aux-b48-cap11",
+                              "vitb-img-b8", "vitb-img-aux-b6-cap41", "vitb-txt-b32-cap13"])
+def test_vit_sized_steps_vs_oracle(kind, size, B, cap, cuda):
+    """The BASELINE model sizes (ViT-S/16: configs[1-2]; ViT-B/16: configs[3]) through the whole fused step, with the
+    persistent kernels forced onto few CTAs (`cap`) so that every GEMM / attention launch of the step walks several
+    tiles / items per CTA, as the B=112 / B=96 bench launches do.  Oracle: fp32 torch on the host cores."""
+    _step_vs_oracle(kind, size, B, cuda, cap)
 
 
 def test_droppath_scales_are_applied(cuda):
