@@ -1,22 +1,29 @@
 """Benchmark of the FedCola round hot path (BASELINE.json metric: local-train samples/s per round @N B200;
 aggregation HBM GB/s).
 
-  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference --gpus N --steps K --warmup W
+  python bench.py --gpus N --steps K --warmup W [--config NAME]      (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W     (the reference's own CPU path, host cores)
 
-A *step* is one full federated round of BASELINE.json configs[1] — FedCola (shared_param=attn,
-share_scope=modality, --compensation --with_aux --aux_trained), ViT-S/16-sized ModalityAgnosticTransformer,
-Flickr30k-shaped synthetic clients: per GPU 12 img + 12 txt + 8 img-txt clients, C=0.25 -> 3+3+2 sampled per
-round, 896 samples each, B=112, E=1, seq_len 64, AdamW lr 1e-4, DropPath 0.1 — through the drop-in
-`FedavgServer.update()`: sampling, download, local training of every sampled client, aggregation of the three
-global models, aux refresh.  N GPUs = N x the clients (weak scaling), sharded by the server, NCCL all-reduce
-of the closed-form partial aggregates.
+A *step* is one full federated round through the drop-in `FedavgServer.update()`: sampling, download, local
+training of every sampled client, aggregation of the global models, aux refresh.  Configurations (`--config`):
+
+  vits-flickr  (default) BASELINE.json configs[1]: FedCola (shared_param=attn, share_scope=modality, --compensation
+               --with_aux --aux_trained), ViT-S/16-sized MAT, per GPU 12 img + 12 txt + 8 img-txt Flickr30k-shaped
+               synthetic clients, C=0.25 -> 3+3+2 sampled per round, 896 samples each, B=112, E=1, seq_len 64, AdamW
+               lr 1e-4, DropPath 0.1.  N GPUs = N x the clients (weak scaling).
+  vits-coco    configs[2]: same model/flags, COCO-shaped, 24+24+16 clients -> 6+6+4 = 16 sampled in TOTAL, B=96,
+               sharded over the N GPUs (strong scaling); --placement reference|balanced.
+  vitb-fediot  configs[3]: ViT-B/16-sized, FedIoT (shared_param=blocks, share_scope=modality_exact), 96+96+64 clients
+  vitb-fedprox -> 24+24+16 = 64 sampled in total, B=96, 384 samples each; FedProx: mu=0.001, none/dataset.
+  agg-sweep    configs[4]: aggregation microbenchmark, K = 8..256 clients x ViT-B arenas, all share_scope modes.
 
 `value`  : samples/s with every client's data resident in HBM (device-timed, max over ranks).
-`e2e`    : same rounds with the data in pinned HOST memory: every step's batch is copied host->device inside
-           the timed region and the per-epoch loss/acc statistics are read back device->host.
-`--impl reference`: the reference's CPU path (oracle port, torch fp32 on the host cores) on a bounded sample of
-the same workload.  Prints ONE JSON line.
+`e2e`    : the same rounds with the data in pinned HOST memory: every batch is copied host->device inside the timed
+           region (double-buffered on a side stream) and the per-epoch loss/acc statistics are read back.
+`--impl reference`: the UNMODIFIED reference (baseline/_ref, installed by oracle/install_ref.py; the six third-party
+modules this image lacks are stubbed by oracle/ref_shim.py) through its own `FedavgServer.update()` on the host cores
+at the same batch size, each step a bounded sample of the workload (one client of each kind x one batch).  Falls back
+to the oracle port when baseline/_ref is absent.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -30,11 +37,62 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu-eager"])
+    ap.add_argument("--config", default="vits-flickr",
+                    choices=["vits-flickr", "vits-coco", "vitb-fediot", "vitb-fedprox", "agg-sweep"])
+    ap.add_argument("--placement", default="reference", choices=["reference", "balanced"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-parity-check", dest="parity", action="store_false")
+    ap.add_argument("--no-gpu-eager", dest="gpu_eager", action="store_false")
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
+    ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
+    ap.add_argument("--ref-samples", type=int, default=0, help="reference arms: samples per client per step (0 = one batch)")
+    ap.add_argument("--ref-budget-s", type=float, default=180.0, help="reference arm: stop timing new steps after this long")
+    ap.add_argument("--sweep-small", action="store_true", help="agg-sweep on ViT-S arenas")
+    return ap.parse_args()
+
+
+ARGS = parse_args()
+if ARGS.impl == "reference":
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""          # the reference's clients go to 'cpu' when no GPU is visible
+if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "src")):
+    os.environ["FEDCOLA_REFERENCE"] = os.path.join(ROOT, "baseline", "_ref")   # never /root/reference at bench time
+
 import torch  # noqa: E402
 
-FLOPS_PER_SAMPLE = {"img": 27.59e9, "txt": 8.38e9, "img+txt": 35.97e9}     # ViT-S fwd+bwd, BASELINE.md §3
-MODEL = "mome_small_patch16"
-B, N_PER_CLIENT, SEQ = 112, 896, 64
+SEQ = 64
+VIT_S = dict(model="mome_small_patch16", d=384, depth=12, heads=6)
+VIT_B = dict(model="mome_base_patch16", d=768, depth=12, heads=12)
+FEDCOLA = dict(algorithm="fedavg", shared_param="attn", share_scope="modality", compensation=True, with_aux=True,
+               aux_trained=True)
+CONFIGS = {
+    # per_gpu: client counts scale with N (weak); total: fixed federation sharded over N (strong)
+    "vits-flickr": dict(VIT_S, flags=FEDCOLA, pair_ds="Flickr30k", B=112, n=896, per_gpu=(12, 12, 8), total=None,
+                        baseline_config="configs[1]"),
+    "vits-coco": dict(VIT_S, flags=FEDCOLA, pair_ds="Coco", B=96, n=768, per_gpu=None, total=(24, 24, 16),
+                      baseline_config="configs[2]"),
+    "vitb-fediot": dict(VIT_B, flags=dict(algorithm="fediot", shared_param="blocks", share_scope="modality_exact"),
+                        pair_ds="Coco", B=96, n=384, per_gpu=None, total=(96, 96, 64), baseline_config="configs[3]"),
+    "vitb-fedprox": dict(VIT_B, flags=dict(algorithm="fedprox", shared_param="none", share_scope="dataset", mu=0.001),
+                         pair_ds="Coco", B=96, n=384, per_gpu=None, total=(96, 96, 64), baseline_config="configs[3]"),
+}
+
+
+def flops_per_sample(cfg, modality):
+    """fwd+bwd FLOPs of one sample: 3*[L(24 N d^2 + 4 N^2 d) + 2*196*768*d (img)]  (SURVEY §8 / BASELINE.md §3)."""
+    d, L = cfg["d"], cfg["depth"]
+
+    def enc(N, img):
+        return 3.0 * (L * (24.0 * N * d * d + 4.0 * N * N * d) + (2.0 * 196 * 768 * d if img else 0.0))
+    return (enc(197, True) if "img" in modality else 0.0) + (enc(SEQ, False) if "txt" in modality else 0.0)
 
 
 def peaks():
@@ -46,20 +104,28 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-def workload_args(n_gpus, **over):
+def workload_args(cfg, counts, **over):
     from fedcola_b200.harness import make_args
-    kw = dict(model_name=MODEL, datasets=["CIFAR100", "AG_NEWS", "Flickr30k", "Coco"],
-              modalities=["img", "txt", "img+txt", "img+txt"], shared_param="attn", share_scope="modality",
-              compensation=True, with_aux=True, aux_trained=True, Ks=[12 * n_gpus, 12 * n_gpus, 8 * n_gpus],
-              K=32 * n_gpus, Cs=[0.25], equal_sampled=True, B=B, E=1, optimizer="AdamW", lr=1e-4, lr_decay=0.99,
-              lr_decay_step=1, seq_len=SEQ, dropout=0.1, no_shuffle=False, num_thread=1, seed=1,
-              out_modality_scales=[1, 1, 1, 1], droppath_rng="fused", data_resident="device")
+    kw = dict(model_name=cfg["model"], datasets=["CIFAR100", "AG_NEWS", cfg["pair_ds"], "Coco"],
+              modalities=["img", "txt", "img+txt", "img+txt"], Ks=list(counts), K=sum(counts), Cs=[0.25],
+              equal_sampled=True, B=cfg["B"], E=1, optimizer="AdamW", lr=1e-4, lr_decay=0.99, lr_decay_step=1,
+              seq_len=SEQ, dropout=0.1, no_shuffle=False, num_thread=1, seed=1, out_modality_scales=[1, 1, 1, 1],
+              droppath_rng="fused", data_resident="device")
+    kw.update(cfg["flags"])
     kw.update(over)
     return make_args(**kw)
 
 
-def client_specs(n_gpus, n=N_PER_CLIENT):
-    return [("CIFAR100", n, 1)] * (12 * n_gpus) + [("AG_NEWS", n, 2)] * (12 * n_gpus) + [("Flickr30k", n, 3)] * (8 * n_gpus)
+def client_specs(cfg, counts, n=None):
+    n = n or cfg["n"]
+    return [("CIFAR100", n, 1)] * counts[0] + [("AG_NEWS", n, 2)] * counts[1] + [(cfg["pair_ds"], n, 3)] * counts[2]
+
+
+def sample_workload(cfg, n, **over):
+    """The bounded sample both reference arms and the parity check run: ONE client of each kind, n samples each,
+    the workload's own batch size / flags / optimizer, deterministic (DropPath 0, no shuffling)."""
+    args = workload_args(cfg, (1, 1, 1), Cs=[1.0], dropout=0.0, no_shuffle=True, **over)
+    return args, client_specs(cfg, (1, 1, 1), n)
 
 
 class NullWriter:
@@ -120,33 +186,61 @@ def _log(msg):
 PREWARM_THREADED = 3
 
 
-def _agg_traffic():
-    """DRAM bytes (read + write) of the round's aggregation launch from the committed ncu capture, or None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_aggregate_traffic.json")
+def _profile_json(name, *keys):
+    """A number from a committed ncu summary (profiles/<name>), or None."""
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             t = json.load(f)
-        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+        return t, [t[k] for k in keys]
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
+
+
+def _agg_traffic():
+    for name in ("r2_aggregate_traffic.json", "r1_aggregate_traffic.json"):
+        t, v = _profile_json(name, "dram_bytes_read", "dram_bytes_write")
+        if v:
+            return int(v[0] + v[1])
+    return None
 
 
 def _gemm_traffic():
-    """DRAM bytes per GEMM launch from the committed ncu capture (profiles/r1_gemm_traffic.json), or (None, why)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        t, v = _profile_json(name, "avg_dram_bytes_per_launch", "source")
+        if v:
+            return round(v[0]), v[1] + " — image-client shapes, cold-cache replays"
+    return None, "no ncu capture committed"
+
+
+def _subprocess_json(extra, timeout, env=None):
+    """Run `python bench.py <extra>` and return its JSON line (or {'error': ...})."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py")] + extra
+    e = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+              "ROLE_RANK", "TORCHELASTIC_RUN_ID", "OMP_NUM_THREADS"):
+        e.pop(k, None)
+    e.update(env or {})
     try:
-        with open(path) as f:
-            t = json.load(f)
-        return round(t["avg_dram_bytes_per_launch"]), t["source"] + " — image-client shapes, cold-cache replays"
-    except (OSError, KeyError, ValueError):
-        return None, "no ncu capture committed"
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=e)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout}s"}
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                pass
+    return {"error": f"rc={r.returncode}: {r.stderr.strip()[-400:]}"}
 
 
+# =====================================================================================================
+# our arm
+# =====================================================================================================
 def run_ours(a):
+    import ctypes
     import torch.distributed as dist
     from fedcola_b200 import _lib
     from fedcola_b200.harness import make_client_datasets
-    from fedcola_b200.server.fedavgserver import FedavgServer
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -156,52 +250,64 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     _log("process group ready")
     n_gpus = max(world, 1)
+    cfg = CONFIGS[a.config]
+    counts = tuple(c * n_gpus for c in cfg["per_gpu"]) if cfg["per_gpu"] else cfg["total"]
+    scaling = "weak" if cfg["per_gpu"] else "strong"
     L = _lib.lib()
-    L.fc_launch_count.restype = __import__("ctypes").c_ulonglong
-    L.fc_gemm_profile_collect.restype = __import__("ctypes").c_longlong
+    L.fc_launch_count.restype = ctypes.c_ulonglong
+    L.fc_gemm_profile_collect.restype = ctypes.c_longlong
     pk = peaks()
 
-    def make_server(resident):
-        args = workload_args(n_gpus, data_resident=resident, server_device=str(dev), num_thread=a.threads)
+    def server_class(args):
+        from importlib import import_module
+        return import_module(f"fedcola_b200.server.{args.algorithm}server").__dict__[f"{args.algorithm.title()}Server"]
+
+    def make_server(resident, args=None, specs=None):
+        # world_size 1: clients stay on THIS GPU even when the node has more (the reference's own multi-GPU mode —
+        # one process, clients on cuda:(i % ngpu) — is exercised by tests/test_multigpu_gpu.py, not timed here)
+        args = args or workload_args(cfg, counts, data_resident=resident, server_device=str(dev), num_thread=a.threads,
+                                     client_devices=[str(dev)], placement=a.placement, precision=a.precision)
         random.seed(args.seed)
         torch.manual_seed(args.seed)
-        cds = make_client_datasets(client_specs(n_gpus), seq_len=SEQ, share=True)
-        return FedavgServer(args=args, writer=NullWriter(), server_dataset=(None, {}), client_datasets=cds,
-                            model_str=MODEL), args
+        cds = make_client_datasets(specs or client_specs(cfg, counts), seq_len=SEQ, share=True)
+        return server_class(args)(args=args, writer=NullWriter(), server_dataset=(None, {}), client_datasets=cds,
+                                  model_str=cfg["model"]), args
 
     def timed_rounds(server, steps, warmup, sampler=None):
-        per, agg_ms, agg_bytes = [], [], []
-        samples = 0
-        phases = {"local_training": 0.0, "aggregation_and_refresh": 0.0}
-        for it in range(warmup + steps):
+        """W untimed rounds, then EXACTLY `steps` rounds bracketed by barrier + synchronize on both sides."""
+        for _ in range(warmup):
             server.round += 1
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            if it == warmup and sampler is not None:
-                sampler.mark_begin()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            e0.record()
-            ids = server.update()
-            e1.record()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            wall = (time.perf_counter() - t0) * 1e3
-            if it >= warmup:
-                # device time of the round; the round also has host work (sampling, planning), so take the
-                # larger of the CUDA-event span and the wall clock between the two synchronisations
-                per.append(max(e0.elapsed_time(e1), wall))
-                la = server.last_aggregation
-                agg_ms.append(la["events"][0].elapsed_time(la["events"][1]))
-                agg_bytes.append(la["bytes"])
-                samples += sum(server.args.E * len(server.clients[i]) for i in ids)
-                for k in phases:
-                    phases[k] += server.phase_ms[k] / steps
-        timed_rounds.phases = phases
-        timed_rounds.per_round = [round(x, 1) for x in per]
-        t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
+            server.update()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.mark_begin()
+        per, agg_ms, agg_bytes, samples = [], [], [], 0
+        phases = {"local_training": 0.0, "aggregation_and_refresh": 0.0}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            server.round += 1
+            tr = time.perf_counter()
+            ids = server.update()                 # ends with a device synchronisation: rounds do not overlap
+            per.append((time.perf_counter() - tr) * 1e3)
+            la = server.last_aggregation
+            agg_ms.append(la["events"][0].elapsed_time(la["events"][1]))
+            agg_bytes.append(la["bytes"])
+            samples += sum(server.args.E * len(server.clients[i]) for i in ids)
+            for k in phases:
+                phases[k] += server.phase_ms[k] / steps
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        # a round also has host work (sampling, planning): the larger of the CUDA-event span and the wall clock
+        total = max(e0.elapsed_time(e1), wall)
+        timed_rounds.phases, timed_rounds.per_round = phases, [round(x, 1) for x in per]
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), samples, agg_ms, agg_bytes
@@ -218,18 +324,35 @@ def run_ours(a):
         torch.cuda.profiler.stop()
         return
 
+    # ---- parity guard: the bounded sample of this workload through OUR server, losses kept for the check against
+    #      the reference's own run of the same sample on the host cores (same seed -> bit-identical initial weights)
+    parity = None
+    n_sample = a.ref_samples or cfg["B"]
+    if a.parity and rank == 0:
+        pargs, pspecs = sample_workload(cfg, n_sample, data_resident="device", server_device=str(dev), num_thread=1,
+                                        client_devices=[str(dev)], precision=a.precision)
+        srv, _ = make_server("device", pargs, pspecs)
+        srv.round = 1
+        ids = srv.update()
+        torch.cuda.synchronize()
+        # {client id: epoch loss} straight from the round's own bookkeeping
+        parity = {"ours": {int(i): float(srv.round_results[i][pargs.E]["loss"]) for i in ids}, "n": n_sample}
+        del srv
+        torch.cuda.empty_cache()
+        _log(f"parity sample round done: {parity['ours']}")
+
     # ---- kernel-side number: client data resident in HBM ---------------------------------------------
     server, args = make_server("device")
     _log("server built (HBM-resident data)")
     sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("FC_BENCH_NO_CLOCKS")) else None
     if sampler is not None:
         sampler.start()        # spawn nvidia-smi now (forking this process mid-run costs ~0.3 s of host time)
-    l0 = L.fc_launch_count()
     # Client worker threads run on their own CUDA streams: torch's caching allocator keeps one pool per stream, so
     # a few extra untimed rounds let every (thread, stream) pool reach its steady size before the W warm-up rounds.
     warm = a.warmup + (PREWARM_THREADED if a.threads > 1 else 0)
+    l0 = L.fc_launch_count()
     total_ms, samples, agg_ms, agg_bytes = timed_rounds(server, a.steps, warm, sampler)
-    launches = (L.fc_launch_count() - l0)
+    launches = L.fc_launch_count() - l0
     _log("timed rounds done")
     clocks = sampler.finish() if sampler is not None else None
     launches_timed = int(launches * a.steps / (a.steps + warm))
@@ -246,147 +369,326 @@ def run_ours(a):
     ids = server.update()
     server.args.num_thread = threads
     torch.cuda.synchronize()
-    import ctypes
     ms, fl = ctypes.c_double(0), ctypes.c_double(0)
     n_gemm = L.fc_gemm_profile_collect(ctypes.byref(ms), ctypes.byref(fl))
     L.fc_gemm_profile(0)
     gemm_tflops = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
-    round_flops = sum(FLOPS_PER_SAMPLE[server.clients[i].modality] * len(server.clients[i]) for i in ids
+    round_flops = sum(flops_per_sample(cfg, server.clients[i].modality) * len(server.clients[i]) for i in ids
                       if server._owner.get(i, 0) == rank)
     agg_gbs = [b / (m * 1e-3) / 1e9 for b, m in zip(agg_bytes, agg_ms) if m > 0]
     agg_best = sorted(agg_gbs)[len(agg_gbs) // 2] if agg_gbs else 0.0
-
-    # ---- end to end: same rounds, client data in pinned host memory (H2D per batch, D2H stats per epoch) ----
     del server
     torch.cuda.empty_cache()
     _log("GEMM profile round done")
-    server2, _ = make_server("host")
-    _log("server built (host-resident data)")
-    e2e_ms, e2e_samples, _, _ = timed_rounds(server2, a.steps, max(warm, 1))
-    per_sample = {"img": 3 * 224 * 224 * 4 + 8, "txt": SEQ * 8 + 8, "img+txt": 3 * 224 * 224 * 4 + SEQ * 8}
-    h2d = sum(per_sample[m] * N_PER_CLIENT * c for m, c in (("img", 3), ("txt", 3), ("img+txt", 2))) * n_gpus
-    d2h = 16 * 8 * n_gpus
-    e2e_value = e2e_samples / (e2e_ms / 1e3)
-    _log("e2e rounds done")
 
+    # ---- end to end: same rounds, client data in pinned host memory (H2D per batch, D2H stats per epoch) ----
+    e2e = None
+    if a.e2e:
+        server2, _ = make_server("host")
+        _log("server built (host-resident data)")
+        e2e_ms, e2e_samples, _, _ = timed_rounds(server2, a.steps, max(warm, 1))
+        per_sample = {"img": 3 * 224 * 224 * 4 + 8, "txt": SEQ * 8 + 8, "img+txt": 3 * 224 * 224 * 4 + SEQ * 8}
+        sampled = [max(int(0.25 * c), 1) for c in counts]
+        h2d = sum(per_sample[m] * cfg["n"] * c for m, c in zip(("img", "txt", "img+txt"), sampled))
+        e2e = {"value": round(e2e_samples / (e2e_ms / 1e3), 2), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 16 * sum(sampled), "per_round_ms": list(timed_rounds.per_round)}
+        del server2
+        torch.cuda.empty_cache()
+        _log("e2e rounds done")
+
+    if world > 1:
+        dist.barrier()
     if rank == 0:
         out = {
             "metric": "local_train_samples_per_s_per_round", "value": round(value, 2), "unit": "samples/s",
             "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(total_ms / a.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "FedCola round: ViT-S/16-sized MAT, shared_param=attn share_scope=modality "
-                                   "+compensation +with_aux +aux_trained; per GPU 12 img + 12 txt + 8 img-txt "
-                                   "Flickr30k-shaped synthetic clients, C=0.25 -> 3+3+2 sampled, 896 samples/client, "
-                                   "B=112, E=1, seq_len 64, AdamW lr 1e-4, drop_path 0.1; step = one server.update()",
-                       "samples_per_round": samples // a.steps, "precision": "bf16 operands / fp32 accumulate, fp32 "
-                       "master weights+optimizer+aggregation", "l2": "inputs larger than L2 (GBs of activations and "
-                       "parameters per round)", "parallelism": f"clients sharded over {n_gpus} GPU(s); {a.threads} client worker thread(s)/GPU "
-                                      f"(args.num_thread), each on its own CUDA stream"},
-            "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": describe(cfg, counts, a), "name": a.config, "baseline_config": cfg["baseline_config"],
+                       "samples_per_round": samples // a.steps,
+                       "precision": ("bf16 operands / fp32 accumulate" if a.precision == "bf16" else
+                                     "fp32-accurate split-operand mode") + ", fp32 master weights+optimizer+aggregation",
+                       "l2": "inputs larger than L2 (GBs of activations and parameters per round)",
+                       "parallelism": f"clients sharded over {n_gpus} GPU(s) ({a.placement} placement); {a.threads} client "
+                                      f"worker thread(s)/GPU (args.num_thread), each on its own CUDA stream"},
             "gpu_launches": launches_timed,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(gemm_tflops, 2),
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(gemm_tflops / pk["tf_sustained"], 4),
-                         "peak_source": pk["src"] + " sustained bf16", "traffic": _gemm_traffic()[0], "traffic_source": _gemm_traffic()[1],
-                         "launches_per_round": int(n_gemm), "avg_launch_us": round(ms.value * 1e3 / max(n_gemm, 1), 2),
-                         "round_model_tflops": round(round_flops * n_gpus / (total_ms / a.steps * 1e-3) / 1e12 / n_gpus, 2)},
+                         "peak_source": pk["src"] + " sustained bf16", "traffic": _gemm_traffic()[0],
+                         "traffic_source": _gemm_traffic()[1], "launches_per_round": int(n_gemm),
+                         "avg_launch_us": round(ms.value * 1e3 / max(n_gemm, 1), 2),
+                         "round_model_tflops": round(round_flops / (total_ms / a.steps * 1e-3) / 1e12, 2),
+                         "round_model_frac": round(round_flops / (total_ms / a.steps * 1e-3) / 1e12 / pk["tf_sustained"], 4)},
             "phase_ms_host_clock": {k: round(v, 2) for k, v in phases.items()},
-            "per_round_ms": per_round_ms, "e2e_per_round_ms": list(timed_rounds.per_round),
+            "per_round_ms": per_round_ms,
             "train_phase_samples_per_s": round(samples / a.steps / (phases["local_training"] * 1e-3), 2),
             "aggregation": {"gbs": round(agg_best, 1), "frac_of_measured_hbm": round(agg_best / pk["hbm"], 4),
                             "bytes_per_round": int(agg_bytes[0]) if agg_bytes else 0,
                             "ms": round(sorted(agg_ms)[len(agg_ms) // 2], 4) if agg_ms else None,
-                            "traffic": _agg_traffic()},
+                            "traffic": _agg_traffic(),
+                            "note": "N=1: one launch, sequential lerp (bit-exact). N>1: local partial sums + NCCL "
+                                    "all-reduce of the compact staging buffer + scatter (whole phase timed)"},
         }
-        if a.cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_sample()
+        if e2e is not None:
+            out["e2e"] = e2e
+        # ---- comparators on this box (N=1 only): the unmodified reference on the host cores and on this GPU ----
+        if n_gpus == 1 and (a.cpu_baseline or a.parity):
+            ref = _subprocess_json(["--impl", "reference", "--config", a.config, "--steps", "1", "--warmup", "0",
+                                    "--ref-samples", str(n_sample)], timeout=900)
+            _log(f"reference CPU sample done: {str(ref)[:300]}")
+            if "cpu_baseline" in ref:
+                out["cpu_baseline"] = ref["cpu_baseline"]
+            else:
+                out["cpu_baseline"] = {"value": None, "error": ref.get("error", "no result")}
+            if parity is not None and "first_round_losses" in ref:
+                theirs = {int(k): v for k, v in ref["first_round_losses"].items()}
+                rel = {i: abs(parity["ours"][i] - theirs[i]) / max(abs(theirs[i]), 1e-30) for i in theirs if i in parity["ours"]}
+                out["parity_check"] = {"what": f"per-client epoch loss of one round on the bounded sample (1 img, 1 txt, 1 img-txt "
+                                               f"client x {n_sample} samples, B={cfg['B']}, same seed/initial weights, DropPath 0) "
+                                               f"vs the {ref.get('cpu_baseline', {}).get('kind', '?')} on the host cores",
+                                       "ours": parity["ours"], "reference": theirs,
+                                       "max_rel_err": round(max(rel.values()), 6) if rel else None, "tolerance": 2e-2,
+                                       "ok": bool(rel) and max(rel.values()) <= 2e-2}
+                if not out["parity_check"]["ok"]:
+                    out["parity_check"]["FAILED"] = "losses differ from the reference beyond 2e-2: the throughput below is not valid"
+        if n_gpus == 1 and a.gpu_eager and os.environ.get("FEDCOLA_REFERENCE"):
+            env = {"CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local]
+                   if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local)}
+            eager = _subprocess_json(["--impl", "reference-gpu-eager", "--config", a.config, "--steps", "2", "--warmup", "1"],
+                                     timeout=900, env=env)
+            _log(f"reference GPU-eager done: {str(eager)[:300]}")
+            out["reference_gpu_eager"] = {k: eager.get(k) for k in ("value", "unit", "ms_per_step", "sample", "error")
+                                          if k in eager}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def oracle_round_server(n_img=32, n_txt=32, n_pair=32, batch=32):
-    """Oracle port of the same round on a bounded sample: one client of each kind."""
-    from fedcola_b200.arena import MatSpec
+def describe(cfg, counts, a):
+    f = cfg["flags"]
+    flags = f"algorithm={f['algorithm']} shared_param={f['shared_param']} share_scope={f['share_scope']}" + \
+        (" +compensation +with_aux +aux_trained" if f.get("with_aux") else "") + (f" mu={f['mu']}" if "mu" in f else "")
+    sampled = [max(int(0.25 * c), 1) for c in counts]
+    return (f"FedCola round ({cfg['baseline_config']}): {cfg['model']} (d={cfg['d']}, L={cfg['depth']}) MAT, {flags}; "
+            f"{counts[0]} img + {counts[1]} txt + {counts[2]} img-txt {cfg['pair_ds']}-shaped synthetic clients"
+            f"{' per ' + str(a.gpus) + ' GPU(s)' if cfg['per_gpu'] else ' in total'}, C=0.25 -> "
+            f"{'+'.join(map(str, sampled))} sampled, {cfg['n']} samples/client, B={cfg['B']}, E=1, seq_len {SEQ}, AdamW lr 1e-4, "
+            "drop_path 0.1; step = one server.update()")
+
+
+# =====================================================================================================
+# reference arms: the unmodified reference (baseline/_ref) or, without it, the oracle port
+# =====================================================================================================
+def reference_server(cfg, args, specs):
+    """The reference's own FedavgServer / FedproxServer on the given workload (oracle/ref_shim.py provides the six
+    third-party modules this image lacks; nothing under baseline/_ref is modified)."""
     from fedcola_b200.harness import make_client_datasets
-    from oracle.round_oracle import OracleServer
+    from oracle import ref_shim
+    ref_shim.install()
+    import src.server.fedavgserver as fs
+    alg = "fedavg" if args.algorithm == "fediot" else args.algorithm     # fediot = fedavg classes + flags (SURVEY F5)
+    args.algorithm = alg
+    if alg == "fedprox":
+        from src.server.fedproxserver import FedproxServer as S
+    else:
+        S = fs.FedavgServer
+    random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    cds = make_client_datasets(specs, seq_len=SEQ, share=True)
+    server = S(args=args, writer=ref_shim.NullWriter(), server_dataset=(None, {}), client_datasets=cds,
+               model_str=cfg["model"])
+    # observe (not alter) what every client.update() returns: the per-client epoch losses of the round
+    server._fc_last_losses = {}
+    for c in server.clients:
+        def observed(orig=c.update, c=c):
+            r = orig()
+            server._fc_last_losses[c.id] = float(r[args.E]["loss"])
+            return r
+        c.update = observed
+    return server
+
+
+def port_server(cfg, args, specs):
+    """Fallback when baseline/_ref is absent: the oracle port of the same round (oracle/round_oracle.py)."""
     import numpy as np
-    args = workload_args(1, Ks=[1, 1, 1], K=3, Cs=[1.0], B=batch, dropout=0.0)
-    cds = make_client_datasets([("CIFAR100", n_img, 1), ("AG_NEWS", n_txt, 2), ("Flickr30k", n_pair, 3)], seq_len=SEQ)
-    specs, init = {}, {}
-    rng = np.random.RandomState(0)
-    for ds, mods, ncls, tasks, vocab in (("CIFAR100", ("img", None), (100, None), ("cls", None), 30522),
-                                         ("AG_NEWS", (None, "txt"), (None, 4), (None, "cls"), 30522),
-                                         ("Flickr30k", ("img", "txt"), (None, None), ("rtv", "rtv"), 7732)):
-        sp = MatSpec(embed_dim=384, depth=12, num_heads=6, modalities=mods, num_classes=ncls, tasks=tasks,
-                     vocab_size=vocab, max_text_len=SEQ, with_aux=True, aux_trained=True, shared_param="attn",
-                     share_scope="modality")
-        specs[ds] = sp
-        st = {}
-        for s in sp.unique_segments():
-            v = (rng.standard_normal(s.numel) * 0.02).astype(np.float32).reshape(s.shape)
-            if "norm" in s.key.lower() and s.key.endswith("weight"):
-                v = v + 1.0
-            if s.key.endswith("cross_modal_scale"):
-                v = np.zeros(s.shape, np.float32)
-            st[s.key] = v
-        init[ds] = st
-    random.seed(1)
-    torch.manual_seed(1)
-    return OracleServer(args, cds, specs, init)
+    from fedcola_b200.arena import MatSpec
+    from fedcola_b200.harness import make_client_datasets, DATASET_VOCAB
+    from fedcola_b200.models import mome
+    from oracle.round_oracle import OracleServer
+    cds = make_client_datasets(specs, seq_len=SEQ)
+    random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    specs_, init = {}, {}
+    for i, ds in enumerate(args.datasets[:-1]):      # same construction order / RNG draws as FedavgServer._init_model
+        args.vocab_size = DATASET_VOCAB.get(ds, 30522)
+        mod = args.modalities[i]
+        kw = dict(pretrained=False, args=args, with_aux=args.with_aux, aux_trained=args.aux_trained)
+        if mod == "img":
+            m = mome.create_model(cfg["model"], num_classes=[100, None], modalities=["img", None], tasks=["cls", None], **kw)
+        elif mod == "txt":
+            m = mome.create_model(cfg["model"], num_classes=[None, 4], modalities=[None, "txt"], tasks=[None, "cls"], **kw)
+        else:
+            m = mome.create_model(cfg["model"], num_classes=[None, None], modalities=["img", "txt"], tasks=["rtv", "rtv"], **kw)
+        specs_[ds] = m.spec
+        init[ds] = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
+    return OracleServer(args, cds, specs_, init)
 
 
-def cpu_baseline_sample():
-    torch.set_num_threads(os.cpu_count() or 1)
-    srv = oracle_round_server(16, 16, 16, 16)
-    srv.round = 1
-    t0 = time.perf_counter()
-    srv.update()
-    dt = time.perf_counter() - t0
-    return {"value": round(srv.timing["samples"] / dt, 3), "unit": "samples/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "one full round of the same FedCola/ViT-S workload on 3 clients (1 img, 1 txt, "
-            "1 img-txt) x 16 samples, B=16, oracle port (torch fp32 CPU)",
-            "train_samples_per_s": round(srv.timing["samples"] / srv.timing["train_s"], 3),
-            "aggregation_gbs": round(srv.timing["agg_bytes"] / srv.timing["agg_s"] / 1e9, 3)}
-
-
-def run_reference(a):
+def run_reference(a, gpu_eager=False):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    cfg = CONFIGS[a.config]
     torch.set_num_threads(os.cpu_count() or 1)
-    n = 16
-    srv = oracle_round_server(n, n, n, n)
-    total, samples = 0.0, 0
-    for it in range(a.warmup + a.steps):
-        srv.round += 1
+    have_ref = bool(os.environ.get("FEDCOLA_REFERENCE"))
+    if gpu_eager:
+        if not have_ref or not torch.cuda.is_available():
+            print(json.dumps({"impl": "reference-gpu-eager", "error": "needs baseline/_ref and a GPU"}))
+            return
+        torch.backends.cuda.matmul.allow_tf32 = False       # the reference's arithmetic: strict fp32 (TF32 off)
+        torch.backends.cudnn.allow_tf32 = False
+        n = cfg["n"]
+    else:
+        n = a.ref_samples or cfg["B"]
+    args, specs = sample_workload(cfg, n, num_thread=1, server_device="cpu", data_resident="host")
+    if gpu_eager:
+        args.dropout, args.no_shuffle = 0.1, False           # the workload's own stochastic settings
+    server = reference_server(cfg, args, specs) if have_ref else port_server(cfg, args, specs)
+    kind = "reference" if have_ref else "port"
+    total, samples, first, steps_done = 0.0, 0, None, 0
+    t_begin = time.perf_counter()
+    warmup = min(a.warmup, 1 if not gpu_eager else a.warmup)   # host cores need no clock / allocator warm-up beyond one round
+    for it in range(warmup + a.steps):
+        server.round += 1
+        if gpu_eager:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        srv.update()
+        ids = server.update()
+        if gpu_eager:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if it >= a.warmup:
+        if first is None:
+            src = server._fc_last_losses if have_ref else server.last_losses
+            first = {int(i): float(v) for i, v in src.items()}
+        if it >= warmup:
             total += dt
-            samples += srv.timing["samples"]
+            samples += sum(args.E * n for _ in ids)
+            steps_done += 1
+            if time.perf_counter() - t_begin + dt > a.ref_budget_s and steps_done < a.steps:
+                break                                     # bounded run: stop before the time budget is exceeded
     v = samples / total
-    sample = f"each step = one full round on 3 clients (1 img, 1 txt, 1 img-txt) x {n} samples, B={n}, oracle port of the reference (torch fp32, CPU)"
-    print(json.dumps({
-        "impl": "reference", "metric": "local_train_samples_per_s_per_round", "value": round(v, 3), "unit": "samples/s",
-        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(total / a.steps * 1e3, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FedCola round, ViT-S/16-sized MAT (same config as the GPU arm), bounded sample", "sample": sample},
-        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    where = (f"this GPU, stock PyTorch eager fp32 (TF32 off), clients on cuda:0, aggregation on the host"
+             if gpu_eager else f"{torch.get_num_threads()} host threads, torch fp32 CPU")
+    sample = (f"each step = one full round of the UNMODIFIED reference ({'baseline/_ref' if have_ref else 'oracle port'}) "
+              f"through its own FedavgServer.update(): 1 img + 1 txt + 1 img-txt client x {n} samples, B={cfg['B']}, "
+              f"{a.config} flags/model/optimizer; {where}")
+    line = {
+        "impl": "reference-gpu-eager" if gpu_eager else "reference",
+        "metric": "local_train_samples_per_s_per_round", "value": round(v, 3), "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": steps_done, "warmup": warmup, "ms_per_step": round(total / max(steps_done, 1) * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak" if cfg["per_gpu"] else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": describe(cfg, tuple(c * a.gpus for c in cfg["per_gpu"]) if cfg["per_gpu"] else cfg["total"], a),
+                   "name": a.config, "baseline_config": cfg["baseline_config"], "sample": sample},
+        "sample": sample,
+        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "first_round_losses": first,
+    }
+    if steps_done < a.steps:
+        line["note"] = f"stopped after {steps_done} of {a.steps} steps: --ref-budget-s {a.ref_budget_s:.0f} s reached"
+    print(json.dumps(line))
+
+
+# =====================================================================================================
+# configs[4]: aggregation microbenchmark
+# =====================================================================================================
+def run_agg_sweep(a):
+    from fedcola_b200 import aggregation as agg
+    from fedcola_b200.arena import MatSpec
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    D, Ld, H = (384, 12, 6) if a.sweep_small else (768, 12, 12)
+    modes = [("none", "dataset", False, False), ("attn", "modality", False, False), ("attn", "modality", True, True),
+             ("blocks", "modality_exact", False, False), ("attn", "all", False, False), ("blocks", "all", False, False)]
+    Ks = [8, 16, 32, 64, 128, 256]
+
+    def spec(kind, sp, sc, aux):
+        kw = dict(embed_dim=D, depth=Ld, num_heads=H, max_text_len=64, with_aux=aux, aux_trained=aux, shared_param=sp,
+                  share_scope=sc)
+        if kind == "img":
+            return MatSpec(modalities=("img", None), num_classes=(100, None), tasks=("cls", None), **kw)
+        if kind == "txt":
+            return MatSpec(modalities=(None, "txt"), num_classes=(None, 4), tasks=(None, "cls"), **kw)
+        return MatSpec(modalities=("img", "txt"), num_classes=(None, None), tasks=("rtv", "rtv"), vocab_size=7732, **kw)
+
+    meta = {"img": ("CIFAR100", "img", "cls"), "txt": ("AG_NEWS", "txt", "cls"), "pair": ("Flickr30k", "img+txt", "img+txt")}
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    rows = []
+    for sp, sc, comp, aux in modes:
+        specs = {k: spec(k, sp, sc, aux) for k in ("img", "txt", "pair")}
+        gl_ar = {k: torch.randn(s.total, device=dev) * 0.02 for k, s in specs.items()}
+        names = []
+        for s in specs.values():
+            for k in s.keys():
+                if k not in names:
+                    names.append(k)
+        scope = agg.init_param_scope(names, sp, sc)
+        flags = dict(args_modalities=["img", "txt", "img+txt", "img+txt"], share_scope_flag=sc, compensation=comp, with_aux=aux)
+        for K in Ks:
+            g = torch.Generator().manual_seed(K)
+            kinds = ["img"] * (3 * K // 8) + ["txt"] * (3 * K // 8)
+            kinds += ["pair"] * (K - len(kinds))
+            if sum(specs[k].total for k in kinds) * 4 / 1e9 > 150:     # SURVEY §8d: img-sized arenas for the largest K
+                kinds = ["img"] * K
+            need = sum(specs[k].total for k in kinds) * 4 / 1e9
+            if need > 150:
+                rows.append(dict(shared_param=sp, share_scope=sc, compensation=comp, aux=aux, K=K, skipped=f"{need:.0f} GB"))
+                continue
+            cl = []
+            for i, k in enumerate(kinds):
+                arena = gl_ar[k] + 0.02 * torch.randn(specs[k].total, device=dev)
+                ds, m, t = meta[k]
+                cl.append(agg.ClientCtx(i, ds, m, t, int(torch.randint(500, 5000, (1,), generator=g)), specs[k], arena))
+            outs = {k: torch.empty_like(v) for k, v in gl_ar.items()}
+            gl = [agg.GlobalCtx(meta[k][0], meta[k][1], "rtv" if k == "pair" else "cls", 1, specs[k], gl_ar[k], outs[k])
+                  for k in ("img", "txt", "pair")]
+            t0 = time.perf_counter()
+            plan = agg.AggregationPlan(gl, cl, scope, mode=agg.LERP, **flags).to_device(dev)
+            plan_ms = (time.perf_counter() - t0) * 1e3
+            ts = []
+            for _ in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                plan.launch()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts[1:])[2] * 1e-3
+            gbs = plan.algorithmic_bytes / t / 1e9
+            rows.append(dict(shared_param=sp, share_scope=sc, compensation=comp, aux=aux, K=K, client_kinds="mixed" if len(set(kinds)) > 1 else "img",
+                             gb=round(plan.algorithmic_bytes / 1e9, 2), ms=round(t * 1e3, 3), gbs=round(gbs, 0),
+                             frac_of_measured_hbm=round(gbs / pk["hbm"], 3), plan_host_ms=round(plan_ms, 1)))
+            _log(str(rows[-1]))
+            del cl, plan, outs, gl
+            torch.cuda.empty_cache()
+    done = [r for r in rows if "gbs" in r]
+    best = max(r["gbs"] for r in done)
+    print(json.dumps({"metric": "aggregation_hbm_gbs", "value": best, "unit": "GB/s", "n_gpus": 1, "higher_is_better": True,
+                      "config": {"workload": f"BASELINE configs[4]: fc_aggregate, K clients x {'ViT-S' if a.sweep_small else 'ViT-B'} "
+                                             "arenas (3/8 img, 3/8 txt, 1/4 img-txt; img-only where the mix exceeds 150 GB), "
+                                             "sizes randint(500,5000), median of 5 L2-flushed launches", "name": "agg-sweep"},
+                      "roofline": {"bound": "hbm", "achieved": best, "peak": pk["hbm"], "unit": "GB/s",
+                                   "frac": round(best / pk["hbm"], 4), "peak_source": pk["src"] + " copy bandwidth"},
+                      "aggregation": {"sweep": rows}}))
 
 
 def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
-    ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
-    a = ap.parse_args()
+    a = ARGS
     # stdout carries exactly ONE line, the JSON result: everything libraries print while running (NCCL's version
     # banner, warnings) is routed to stderr at file-descriptor level, and fd 1 is handed back for the final print.
     sys.stdout.flush()
@@ -401,9 +703,13 @@ def main():
         sys.stdout.flush()
         os.dup2(2, 1)
 
-    globals()["print"] = emit            # run_ours / run_reference print only their JSON line
-    if a.impl == "reference":
+    globals()["print"] = emit            # the run_* functions print only their JSON line
+    if a.config == "agg-sweep":
+        run_agg_sweep(a)
+    elif a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-gpu-eager":
+        run_reference(a, gpu_eager=True)
     else:
         run_ours(a)
 

@@ -61,6 +61,8 @@ class GlobalCtx:
     spec: MatSpec
     arena_in: torch.Tensor          # old global (flat fp32)
     arena_out: torch.Tensor         # new global (may be the same tensor)
+    out_offset_of: Optional[Dict[str, int]] = None   # key -> float offset inside arena_out when it is NOT laid out
+                                                     # like the spec's arena (the compact multi-rank staging buffer)
 
 
 @dataclass
@@ -75,8 +77,14 @@ class ClientCtx:
 
 
 def _client_coefs(scope, pm, g: GlobalCtx, clients: List[ClientCtx], modalities, share_scope_flag, compensation,
-                  fedavg):
-    """{client id: python float} for one (global, scope, param-modality) class — fedavgserver.py:601-653."""
+                  fedavg, stale_id=None):
+    """{client id: python float} for one (global, scope, param-modality) class — fedavgserver.py:601-653.
+
+    `stale_id`: the value the reference's loop variable `identifier` still holds at :648 — the LAST key of its
+    `updated_sizes` dict.  Called directly with an ascending dict (CreamflServer, the golden tests) that is the
+    highest id; inside `update()` the dict is `dict(ChainMap(*results))`, which lists clients in REVERSED completion
+    order, so with sequential clients (`--num_thread 1`) it is the lowest sampled id, and with worker threads it is
+    whichever client finished first (the reference is racy there).  None = highest id."""
     sizes = {c.id: c.size for c in clients}
     byid = {c.id: c for c in clients}
     num = {}
@@ -109,7 +117,7 @@ def _client_coefs(scope, pm, g: GlobalCtx, clients: List[ClientCtx], modalities,
             comp = sum(s for i, s in sizes.items()
                        if byid[i].modality in g.modality or g.modality in byid[i].modality)
         elif share_scope_flag == "modality_exact":
-            last = clients[-1]        # stale loop variable `identifier` of the reference (:648), reproduced
+            last = byid[stale_id] if stale_id is not None else clients[-1]    # stale `identifier` (:648), reproduced
             comp = sum(s for i, s in sizes.items() if byid[i].modality == pm or pm in last.modality)
         else:
             raise KeyError("--compensation needs share_scope in {all, modality, modality_exact} "
@@ -152,20 +160,21 @@ class AggregationPlan:
 
     def __init__(self, globals_: List[GlobalCtx], clients: List[ClientCtx], param_scope: Dict[str, str],
                  args_modalities, share_scope_flag, compensation, with_aux, mode=LERP, fedavg=False,
-                 include_global_term=True):
+                 include_global_term=True, stale_id=None):
         clients = sorted(clients, key=lambda c: c.id)
         self.mode = mode
         if mode == LERP and any(c.arena is None for c in clients):
             raise ValueError("sequential-lerp aggregation needs every sampled client's arena on this GPU; "
                              "use mode=WSUM for clients sharded across ranks")
-        sig = (mode, bool(fedavg), bool(include_global_term), tuple(args_modalities), share_scope_flag,
+        sig = (mode, bool(fedavg), bool(include_global_term), stale_id, tuple(args_modalities), share_scope_flag,
                bool(compensation), bool(with_aux), id(param_scope), len(param_scope),
-               tuple((g.spec.signature, g.dataset, g.modality, g.task, g.out_modality_scale) for g in globals_),
+               tuple((g.spec.signature, g.dataset, g.modality, g.task, g.out_modality_scale, g.out_offset_of is not None)
+                     for g in globals_),
                tuple((c.spec.signature, c.dataset, c.modality, c.task, c.size, c.arena is None) for c in clients))
         sym = _PLAN_CACHE.get(sig)
         if sym is None:
             sym = self._build_symbolic(globals_, clients, param_scope, args_modalities, share_scope_flag, compensation,
-                                       with_aux, mode, fedavg, include_global_term)
+                                       with_aux, mode, fedavg, include_global_term, stale_id)
             sym["_pin"] = param_scope            # the key holds its id(): keep it alive
             if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
                 _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
@@ -179,7 +188,7 @@ class AggregationPlan:
         cbase = np.asarray([c.arena.data_ptr() if c.arena is not None else 0 for c in clients] + [0], dtype=np.uint64)
         self.host = dict(
             job_tile_start=sym["job_tile_start"], job_numel=sym["job_numel"], job_nout=sym["job_nout"],
-            job_gin=gin[sym["job_g"]] + sym["job_g_off"], job_gout=gout[sym["job_g"]] + sym["job_g_off"],
+            job_gin=gin[sym["job_g"]] + sym["job_g_off"], job_gout=gout[sym["job_g"]] + sym["job_g_off_out"],
             job_gscale=sym["job_gscale"], job_src_start=sym["job_src_start"],
             src_ptr=cbase[sym["src_owner"]] + sym["src_off"], src_flag=sym["src_flag"],
             scale_ptr=cbase[sym["scale_owner"]] + sym["scale_off"], coef=sym["coef"],
@@ -189,7 +198,7 @@ class AggregationPlan:
 
     @staticmethod
     def _build_symbolic(globals_, clients, param_scope, args_modalities, share_scope_flag, compensation, with_aux,
-                        mode, fedavg, include_global_term):
+                        mode, fedavg, include_global_term, stale_id=None):
         tile = int(_lib.lib().fc_aggregate_tile_floats())
         coef_cache = {}
         ukeys = {c.id: upload_keys(c.spec, with_aux, c.modality) for c in clients}
@@ -206,7 +215,7 @@ class AggregationPlan:
                     names.append(kk)
                 outs[kk].append(gi)
 
-        job_numel, job_nout, job_g, job_g_off, job_gscale = [], [], [], [], []
+        job_numel, job_nout, job_g, job_g_off, job_g_off_out, job_gscale = [], [], [], [], [], []
         job_src_start, src_owner, src_off, src_flag, scale_owner, scale_off, coef = [0], [], [], [], [], [], []
         job_names = []
         algorithmic_bytes = 0
@@ -223,7 +232,7 @@ class AggregationPlan:
                                             (compensation and share_scope_flag == "modality_exact")) else None)
                     if ck not in coef_cache:
                         coef_cache[ck] = _client_coefs(scope, pm, g, clients, args_modalities, share_scope_flag,
-                                                       compensation, fedavg)
+                                                       compensation, fedavg, stale_id)
                     cs.append(coef_cache[ck])
                 rows = []
                 for c in clients:
@@ -257,10 +266,14 @@ class AggregationPlan:
                 job_nout.append(len(gs))
                 for o in range(MAX_OUT):
                     if o < len(gs):
-                        job_g.append(gs[o]), job_g_off.append(globals_[gs[o]].spec.seg(name).offset * 4)
+                        go = globals_[gs[o]]
+                        job_g.append(gs[o]), job_g_off.append(go.spec.seg(name).offset * 4)
+                        job_g_off_out.append((go.out_offset_of[name] if go.out_offset_of is not None
+                                              else go.spec.seg(name).offset) * 4)
                         job_gscale.append(gsc[o])
                     else:
-                        job_g.append(NONE_G), job_g_off.append(0), job_gscale.append(np.float32(0))
+                        job_g.append(NONE_G), job_g_off.append(0), job_g_off_out.append(0)
+                        job_gscale.append(np.float32(0))
                 for c, off, aux, cvals in rows:
                     cpad = cvals + [np.float32(0)] * (MAX_OUT - len(cvals))
                     if aux:      # upload() hands the server W + A*s: a HOLD entry (W) then a MERGE entry (A, s)
@@ -284,6 +297,7 @@ class AggregationPlan:
             job_numel=np.asarray(job_numel, dtype=np.int64),
             job_nout=np.asarray(job_nout, dtype=np.int32),
             job_g=np.asarray(job_g, dtype=np.int64), job_g_off=np.asarray(job_g_off, dtype=np.uint64),
+            job_g_off_out=np.asarray(job_g_off_out, dtype=np.uint64),
             job_gscale=np.asarray(job_gscale, dtype=np.float32),
             job_src_start=np.asarray(job_src_start, dtype=np.int32),
             src_owner=np.asarray(src_owner, dtype=np.int64), src_off=np.asarray(src_off, dtype=np.uint64),
@@ -330,26 +344,91 @@ def shard_owner(position, world_size):
     return position % world_size
 
 
+def place_clients(costs, n_slots, rule="reference"):
+    """Slot (rank, or GPU of a single process) for every position of the sorted sampled-id list.
+
+    rule='reference': position % n_slots — the reference's only rule (fedavgserver.py:310-311).
+    rule='balanced' : longest-processing-time greedy on `costs` (n_k * E * train FLOPs per sample): an
+                      img+txt ViT-S sample costs 36.0 GF against 8.4 GF for a text sample, so position % n leaves
+                      ranks up to ~1.8x apart (6 img + 6 txt + 4 pair clients over 8 ranks).  Sampling and ids are
+                      unaffected; only where a client trains changes.  Deterministic: ties break on position."""
+    n = len(costs)
+    if rule == "reference" or n_slots <= 1:
+        return [shard_owner(i, max(n_slots, 1)) for i in range(n)]
+    if rule != "balanced":
+        raise ValueError(f"unknown placement rule {rule!r} (reference | balanced)")
+    load = [0.0] * n_slots
+    count = [0] * n_slots
+    out = [0] * n
+    for i in sorted(range(n), key=lambda i: (-float(costs[i]), i)):
+        r = min(range(n_slots), key=lambda r: (load[r], count[r], r))
+        out[i] = r
+        load[r] += float(costs[i])
+        count[r] += 1
+    return out
+
+
+def train_flops_per_sample(spec: MatSpec, modality: str):
+    """fwd+bwd FLOPs of one sample, 3 * [L(24 N d^2 + 4 N^2 d) + patch embed]  (SURVEY §8 table)."""
+    d, L = spec.embed_dim, spec.depth
+
+    def enc(N, img):
+        return 3.0 * (L * (24.0 * N * d * d + 4.0 * N * N * d) + (2.0 * spec.num_patches * 768 * d if img else 0.0))
+    f = 0.0
+    if "img" in modality:
+        f += enc(spec.num_patches + 1, True)
+    if "txt" in modality:
+        f += enc(spec.max_text_len, False)
+    return f
+
+
+_STAGE_CACHE = {}
+
+
+def _staging_for(globals_):
+    """Persistent compact staging buffer of the multi-rank aggregation: the `required_keys()` segments of every
+    global model back to back (each padded to 32 floats) — what actually has to cross NVLink (ViT-S FedCola:
+    403 MB instead of the 573 MB of whole arenas with their aux_weight copies).  Built once per set of global
+    arenas; returns (buffer, per-global {key: float offset}, arena views, staging views)."""
+    key = tuple((g.arena_in.data_ptr(), g.spec.signature) for g in globals_)
+    st = _STAGE_CACHE.get(key)
+    if st is None:
+        offs, total = [], 0
+        for g in globals_:
+            o = {}
+            for k in g.spec.required_keys():
+                o[k] = total
+                total += (g.spec.seg(k).numel + 31) // 32 * 32
+            offs.append(o)
+        buf = torch.zeros(max(total, 32), dtype=torch.float32, device=globals_[0].arena_in.device)
+        dsts, srcs = [], []
+        for g, o in zip(globals_, offs):
+            for k, so in o.items():
+                sg = g.spec.seg(k)
+                dsts.append(g.arena_in[sg.offset:sg.offset + sg.numel])
+                srcs.append(buf[so:so + sg.numel])
+        _STAGE_CACHE.clear()                       # one live federation per process
+        st = _STAGE_CACHE[key] = (buf, offs, dsts, srcs)
+    return st
+
+
 def sharded_aggregate(globals_, clients, param_scope, flags, dist, rank, execute=None):
     """Multi-GPU aggregation: every rank folds ITS clients (those with an arena) into closed-form
-    partial sums, one all-reduce (NCCL over NVLink on the GPU box; gloo in the CPU tests) finishes them, and
-    every rank ends with the same new global arenas.  `execute(plan)` runs the plan tables (default: the
-    CUDA kernel).  Returns the plan (for byte accounting)."""
-    parts = []
-    for g in globals_:
-        # regions the plan does not write (aux_weight, cross_modal_scale, padding) must survive the sum:
-        # rank 0 contributes the old arena, the others zeros
-        part = g.arena_in.clone() if rank == 0 else torch.zeros_like(g.arena_in)
-        g.arena_out = part
-        parts.append(part)
+    partial sums written straight into a persistent compact staging buffer (rank 0 also adds the old-global term,
+    the other ranks start from zero inside the kernel — no clone / memset), ONE all-reduce over that buffer (NCCL
+    over NVLink on the GPU box; gloo in the CPU tests) finishes the sums, and one multi-tensor copy scatters them
+    into the global arenas; aux_weight / cross_modal_scale / padding are never touched.  `execute(plan)` runs the
+    plan tables (default: the CUDA kernel).  Returns the plan (for byte accounting)."""
+    buf, offs, dsts, srcs = _staging_for(globals_)
+    for g, o in zip(globals_, offs):
+        g.arena_out, g.out_offset_of = buf, o
     plan = AggregationPlan(globals_, clients, param_scope, mode=WSUM, include_global_term=(rank == 0), **flags)
     if execute is None:
-        plan.to_device(globals_[0].arena_in.device).launch()
+        plan.to_device(buf.device).launch()
     else:
         execute(plan)
-    works = [dist.all_reduce(p, op=dist.ReduceOp.SUM, async_op=True) for p in parts]
-    for w in works:
-        w.wait()
-    for g, p in zip(globals_, parts):
-        g.arena_in.copy_(p)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    with torch.no_grad():
+        torch._foreach_copy_(dsts, srcs)
+    plan.allreduce_bytes = buf.numel() * 4
     return plan

@@ -18,47 +18,116 @@ from .. import runtime as R
 logger = logging.getLogger(__name__)
 
 
-class _StagedData:
-    """The client's training set as whole tensors (pinned host memory or HBM), built once.
-    Items follow the reference datasets: (x, y) or (img, ids, img_id, idx, idx)."""
+def _as_model_input(t, is_float):
+    """Inputs reach the kernels as raw pointers: images fp32, token ids / labels int64, contiguous."""
+    t = torch.as_tensor(t)
+    return t.to(torch.float32 if is_float else torch.int64).contiguous()
 
-    def __init__(self, dataset, modality, resident, device):
-        n = len(dataset)
+
+def epoch_batches(index_loader):
+    """The batches of one epoch as index lists, drawn EXACTLY as the reference's `for batch in self.train_loader`
+    draws them (fedavgclient.py:79): a real DataLoader iterator over range(n) consumes the global torch RNG the same
+    way (the iterator's `_base_seed` draw, then the RandomSampler's seed draw), so shuffled batch order and every
+    later draw from the global stream agree with the reference under the same seed."""
+    return [t.tolist() for t in index_loader]
+
+
+class _ClientData:
+    """A client's training set as the hot loop consumes it.
+
+    Tensor-backed sets (the dataset exposes whole tensors `x`/`y`, `x`/`ids` or `a`/`b`: the synthetic benchmark
+    sets and the test fixtures) are staged once — pinned host memory, or HBM with args.data_resident='device'.
+    Any other dataset goes through `__getitem__` for EVERY batch of every epoch, like the reference's DataLoader, so
+    stochastic train-time transforms (RandomCrop / flips / ColorJitter, src/loaders/data.py:95-105) are re-drawn;
+    `args.cache_dataset=True` opts into materialising it once."""
+
+    def __init__(self, dataset, modality, resident, device, cache_items=False):
+        self.dataset, self.modality, self.resident, self.device = dataset, modality, resident, device
+        self.n = len(dataset)
+        self.float_cols = (True, False) if modality != "txt" else (False, False)
         cols = None
         for name_a, name_b in (("x", "ids" if modality == "img+txt" else "y"), ("a", "b")):
             if hasattr(dataset, name_a) and hasattr(dataset, name_b):
                 cols = [getattr(dataset, name_a), getattr(dataset, name_b)]
                 break
-        if cols is None:      # generic path: materialise through __getitem__ once
-            items = [dataset[i] for i in range(n)]
+        if cols is None and cache_items:
+            items = [dataset[i] for i in range(self.n)]
             cols = [torch.stack([torch.as_tensor(it[0]) for it in items]),
                     torch.stack([torch.as_tensor(it[1]) for it in items])]
-        self.cols = []
-        for c in cols:
-            c = c.contiguous()
-            if resident == "device":
-                c = c.to(device)
-            elif torch.cuda.is_available():
-                c = c.pin_memory()
-            self.cols.append(c)
-        self.resident, self.device, self.n = resident, device, n
+        self.cols = None
+        if cols is not None:
+            self.cols = []
+            for c, fl in zip(cols, self.float_cols):
+                c = _as_model_input(c, fl)
+                if resident == "device":
+                    c = c.to(device)
+                elif torch.cuda.is_available() and not c.is_pinned():
+                    c = c.pin_memory()
+                self.cols.append(c)
 
-    def open(self):
-        """Device view of the data for one update(): the HBM-resident tensors, or (host-resident) one async
-        host->device copy of the client's set from pinned memory on the current stream — batches are then
-        gathered on the GPU instead of being fancy-indexed by the CPU."""
-        if self.resident == "device":
-            return self.cols
-        return [c.to(self.device, non_blocking=True) for c in self.cols]
+    def _collate(self, idx):
+        items = [self.dataset[i] for i in idx]
+        out = []
+        for j, fl in enumerate(self.float_cols):
+            t = _as_model_input(torch.stack([torch.as_tensor(it[j]) for it in items]), fl)
+            out.append(t.pin_memory() if torch.cuda.is_available() else t)
+        return out
 
-    @staticmethod
-    def batch(dev_cols, idx):
-        """idx: list[int] (from the DataLoader's own batch sampler) -> contiguous device tensors."""
-        contiguous = len(idx) > 0 and idx == list(range(idx[0], idx[0] + len(idx)))
-        if contiguous:
-            return [c[idx[0]:idx[0] + len(idx)] for c in dev_cols]
-        ix = torch.as_tensor(idx, device=dev_cols[0].device)
-        return [c.index_select(0, ix) for c in dev_cols]
+    def feed(self, batches):
+        """Yields (a, b) device tensors for every index list of `batches`.
+
+        HBM-resident sets: slices / one on-device gather.  Host-resident sets: the batch after the one being trained
+        on is copied host->device on a side stream into the other of two device buffers (fc_h2d_rows: one
+        cudaMemcpyAsync per run of consecutive rows), so the copies hide under compute and only two batches of
+        inputs ever occupy HBM."""
+        if self.cols is not None and self.resident == "device":
+            for idx in batches:
+                contiguous = len(idx) > 0 and idx == list(range(idx[0], idx[0] + len(idx)))
+                if contiguous:
+                    yield [c[idx[0]:idx[0] + len(idx)] for c in self.cols]
+                else:
+                    ix = torch.as_tensor(idx, device=self.cols[0].device)
+                    yield [c.index_select(0, ix) for c in self.cols]
+            return
+        if not batches:
+            return
+        from .. import _lib
+        L = _lib.lib()
+        dev = torch.device(self.device)
+        compute = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        bmax = max(len(b) for b in batches)
+        probe = self.cols if self.cols is not None else self._collate(batches[0][:1])
+        slots = [[torch.empty((bmax,) + tuple(c.shape[1:]), dtype=c.dtype, device=dev) for c in probe] for _ in range(2)]
+        free_ev, ready_ev, keep = [None, None], [None, None], [None, None]
+
+        def issue(k):
+            slot, idx = k % 2, batches[k]
+            host = None if self.cols is not None else self._collate(idx)
+            with torch.cuda.stream(side):
+                if free_ev[slot] is not None:
+                    side.wait_event(free_ev[slot])
+                if host is not None:
+                    for dst, src in zip(slots[slot], host):
+                        dst[:len(idx)].copy_(src, non_blocking=True)
+                    keep[slot] = host
+                else:
+                    ix = torch.as_tensor(idx, dtype=torch.int64)
+                    for dst, src in zip(slots[slot], self.cols):
+                        row = src[0].numel() * src.element_size() if src.dim() > 1 else src.element_size()
+                        _lib.check(L.fc_h2d_rows(_lib.ptr(dst), _lib.ptr(src), _lib.c_vp(ix.data_ptr()), _lib.c_int(len(idx)),
+                                                 _lib.c_ll(row), _lib.c_int(dev.index), _lib.c_vp(side.cuda_stream)),
+                                   "fc_h2d_rows")
+                ready_ev[slot] = side.record_event()
+
+        issue(0)
+        for k, idx in enumerate(batches):
+            if k + 1 < len(batches):
+                issue(k + 1)
+            compute.wait_event(ready_ev[k % 2])
+            yield [c[:len(idx)] for c in slots[k % 2]]
+            free_ev[k % 2] = compute.record_event()        # the step that consumed this slot has been enqueued
+        side.synchronize()
 
 
 class FedavgClient(BaseClient):
@@ -74,6 +143,8 @@ class FedavgClient(BaseClient):
             raise NotImplementedError(f"fedcola_b200: criterion {criterion!r} has no sm_100a kernel "
                                       "(supported: CrossEntropyLoss, ContrastiveLoss)")
         self.train_loader = self._create_dataloader(self.training_set, shuffle=not self.args.no_shuffle)
+        # same batch size / shuffle flag over the sample indices: iterating it draws what iterating train_loader draws
+        self._index_loader = self._create_dataloader(range(len(self.training_set)), shuffle=not self.args.no_shuffle)
         self.test_loader = self._create_dataloader(self.test_set, shuffle=False, test=True) \
             if self.test_set is not None else None
         self.task = task
@@ -116,9 +187,13 @@ class FedavgClient(BaseClient):
         if self.args.distributed or (self.args.mm_distributed and self.modality == "img+txt"):
             raise NotImplementedError("nn.DataParallel inside a client is replaced by client sharding across GPUs")
         resident = getattr(self.args, "data_resident", "host")
-        cache = self.training_set.__dict__.setdefault("_fc_staged", {})     # shared by clients sharing a dataset
+        try:
+            cache = self.training_set.__dict__.setdefault("_fc_staged", {})  # shared by clients sharing a dataset
+        except AttributeError:
+            cache = {}
         if (resident, str(dev)) not in cache:
-            cache[(resident, str(dev))] = _StagedData(self.training_set, self.modality, resident, dev)
+            cache[(resident, str(dev))] = _ClientData(self.training_set, self.modality, resident, dev,
+                                                      cache_items=getattr(self.args, "cache_dataset", False))
         data = self._staged = cache[(resident, str(dev))]
         with torch.cuda.device(dev):
             trainer = self.trainer = self._make_trainer()        # fresh optimizer state every round (:63)
@@ -126,15 +201,14 @@ class FedavgClient(BaseClient):
             kind = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}[self.modality]
             rng_mode = getattr(self.args, "droppath_rng", "fused")
             results = {}
-            dev_cols = data.open()
             logger.info(f"[{self.task.upper()}] [{self.modality.upper()}] ...working on client {self.id}... ")
             for e in range(self.args.E):
                 trainer.stats.zero_()
                 num = seen = 0
-                for idx in self.train_loader.batch_sampler:     # same sampler => same shuffling RNG as the reference
-                    if num >= 2 and self.args.debug:
-                        break
-                    a, b = data.batch(dev_cols, idx)
+                batches = epoch_batches(self._index_loader)     # the reference's DataLoader draws, exactly
+                if self.args.debug:
+                    batches = batches[:2]
+                for idx, (a, b) in zip(batches, data.feed(batches)):
                     dp = R.droppath_scales(spec, len(idx), dev, True, rng_mode)
                     if self.modality == "img":
                         trainer.step(a, None, b, kind, dp)
@@ -152,7 +226,6 @@ class FedavgClient(BaseClient):
                 results[e + 1] = res
                 logger.info(f"[Client {self.id}] loss: {res['loss']}" +
                             (f", acc1: {res['metrics'].get('acc1')}" if self.modality != "img+txt" else ""))
-            del dev_cols
         return results
 
     @torch.inference_mode()

@@ -781,7 +781,11 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
   const int buf_bytes = 3 * NK * 128, aux = 6144 + 128;
   int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
   while (nbuf > 1 && nbuf * buf_bytes + aux > kMaxDynSmem) --nbuf;
-  const int smem = nbuf * buf_bytes + aux;
+  // QK^T is issued with M = 128 whatever N is: the tensor core reads 128 rows (16 KB) from the Q tile's address.  Rows
+  // past the item's NK only produce score rows nobody reads, but for very short sequences (NK = 16: a 6 KB buffer)
+  // the read from the LAST buffer would run past the CTA's shared-memory allocation -> pad the allocation.
+  const int pad = buf_bytes < TILE ? TILE - buf_bytes : 0;
+  const int smem = nbuf * buf_bytes + aux + pad;
   FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
   const int items = B * H;
   const int sms = fc_num_sms(device);

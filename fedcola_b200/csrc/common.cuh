@@ -5,10 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define FC_OK 0
-#define FC_ERR_INVALID (-1)
-#define FC_ERR_CUDA (-2)
-#define FC_ERR_UNSUPPORTED (-3)
+#include "../../include/fedcola_b200.h"   // FC_OK / FC_ERR_* and the entry-point declarations
 
 // Last error text, per thread (entry points are called from the reference's ThreadPoolExecutor workers).
 extern thread_local char fc_last_error_buf[512];

@@ -264,6 +264,7 @@ def _factory(embed_dim, depth, num_heads):
 # the reference's factories (mome.py:924-1033) + the sizes BASELINE.json names that have no factory upstream
 for _name, _cfg in {"mome_small_patch16": (384, 12, 6), "mome_tiny_patch16": (192, 12, 3),
                     "mome_small_patch16_224_in21k": (384, 12, 6), "mome_base_patch16_224_ours": (768, 12, 12),
+                    "mome_toy_patch16_224": (4, 1, 2),        # mome.py:1016 (head_dim 2: constructs, cannot run here)
                     "mome_base_patch16": (768, 12, 12), "mome_d192_l4": (192, 4, 3),
                     "mome_d64_l2": (64, 2, 1)}.items():
     _f = _factory(*_cfg)

@@ -8,8 +8,13 @@ Same constructor, attributes (`global_models`, `param_scope`, `clients`, `curr_l
   * `_aggregate` for ALL global models is ONE streaming kernel launch (fedcola_b200.aggregation ->
     csrc/aggregate.cu) that reproduces the reference's sequential lerp bit for bit;
   * with torch.distributed initialised (one process per GPU, NCCL), sampled clients are sharded across ranks
-    (position i -> rank i % world_size, the reference's `cuda:(i % ngpu)` rule, :310-311), every rank reduces
-    its own clients in closed form and one all-reduce over NVLink finishes the sum.
+    (position i -> rank i % world_size, the reference's `cuda:(i % ngpu)` rule, :310-311; or cost-balanced with
+    `args.placement='balanced'`), every rank reduces its own clients in closed form and one all-reduce over
+    NVLink finishes the sum (SURVEY §8e);
+  * in a single process with several visible GPUs — the reference's own multi-GPU mode: worker threads, client
+    i on `cuda:(i % ngpu)` (:310-311, 560-577) — clients train on their GPU and the aggregation kernel on the
+    server GPU reads their arenas in place through NVLink peer access: the sequential lerp stays bit-exact.
+    `args.client_devices` (a list of device strings) restricts the GPUs clients are placed on.
 
 Client sampling, coefficient bookkeeping, lr decay and result logging are kept in Python, unchanged."""
 import concurrent.futures
@@ -60,7 +65,12 @@ class FedavgServer(BaseServer):
         self.round = 0
         d = _dist()
         self.rank, self.world_size = (d.get_rank(), d.get_world_size()) if d else (0, 1)
+        if getattr(self.args, "mp", False):
+            raise NotImplementedError("fedcola_b200: --mp (ProcessPoolExecutor clients, fedavgserver.py:560-562) is "
+                                      "replaced by one process per GPU under torchrun; run without --mp")
         self.server_device = self._resolve_device(self.args.server_device)
+        self._client_devices = self._resolve_client_devices()
+        self._peer = {}
         if self.args.eval_type != "local":
             self._set_loaders(server_dataset)
         self.global_models = self._init_model(model_str)
@@ -92,10 +102,45 @@ class FedavgServer(BaseServer):
         dev = torch.device(name if str(name).startswith("cuda") else "cuda:0")
         return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
 
-    def _client_device(self, position):
+    def _resolve_client_devices(self):
+        """GPUs that clients are placed on.  One process per GPU (torchrun): the rank's own GPU.  Single process:
+        every visible GPU, as the reference does (`'cuda:%d' % (i % torch.cuda.device_count())`, :310-311), unless
+        `args.client_devices` narrows the list."""
         if self.world_size > 1:
-            return str(self.server_device)
-        return "cuda:%d" % (position % torch.cuda.device_count())
+            return [str(self.server_device)]
+        devs = getattr(self.args, "client_devices", None)
+        if devs:
+            out = []
+            for d in devs:
+                dv = torch.device(d)
+                if dv.type != "cuda":
+                    raise RuntimeError(f"fedcola_b200: client device {d!r} is not a CUDA device (no CPU path)")
+                idx = dv.index if dv.index is not None else torch.cuda.current_device()
+                if idx >= torch.cuda.device_count():
+                    raise RuntimeError(f"fedcola_b200: client device {d!r} does not exist "
+                                       f"({torch.cuda.device_count()} visible GPU(s))")
+                out.append("cuda:%d" % idx)
+            return out
+        return ["cuda:%d" % i for i in range(torch.cuda.device_count())]
+
+    def _client_device(self, slot):
+        return self._client_devices[slot % len(self._client_devices)]
+
+    def _peer_readable(self, device):
+        """True when kernels on the server GPU can dereference memory of `device` (NVLink / PCIe peer access)."""
+        idx = device.index
+        if idx == self.server_device.index:
+            return True
+        if idx not in self._peer:
+            from .. import _lib
+            rc = _lib.lib().fc_enable_peer_access(int(self.server_device.index), int(idx))
+            if rc not in (0, -3):
+                _lib.check(rc, "fc_enable_peer_access")
+            self._peer[idx] = rc == 0
+            if rc != 0:
+                logger.warning(f"no peer access {self.server_device} -> cuda:{idx}: client arenas from that GPU are "
+                               "copied to the server GPU before aggregation")
+        return self._peer[idx]
 
     # ---- construction ---------------------------------------------------------------------------------
     def _init_model(self, model_str):
@@ -181,11 +226,28 @@ class FedavgServer(BaseServer):
                         [i for i in range(self.args.K) if i not in exclude], num_sampled_clients))
         if self.args.warmup_modality != "none" and self.round <= self.args.warmup_rounds:
             sampled_client_ids = [i for i in sampled_client_ids if self.clients[i].modality == self.args.warmup_modality]
-        self._owner = {}
-        for i, cid in enumerate(sampled_client_ids):
-            self.clients[cid].device = self._client_device(i)
-            self._owner[cid] = agg.shard_owner(i, self.world_size)
+        self._place(sampled_client_ids)
         return sampled_client_ids
+
+    def _place(self, sampled_client_ids):
+        """Where each sampled client trains: its rank (one process per GPU) or its GPU (single process).  The rule is
+        the reference's position % n (:310-311) or, with args.placement='balanced', a cost-balanced assignment."""
+        rule = getattr(self.args, "placement", "reference")
+        costs = None
+        if rule != "reference":
+            costs = [len(self.clients[c]) * self.args.E *
+                     agg.train_flops_per_sample(self.global_models[self.clients[c].dataset].spec, self.clients[c].modality)
+                     for c in sampled_client_ids]
+        n_slots = self.world_size if self.world_size > 1 else len(self._client_devices)
+        slots = agg.place_clients(costs if costs is not None else [0] * len(sampled_client_ids), n_slots, rule)
+        self._owner = {}
+        for cid, slot in zip(sampled_client_ids, slots):
+            if self.world_size > 1:
+                self.clients[cid].device = str(self.server_device)
+                self._owner[cid] = slot
+            else:
+                self.clients[cid].device = self._client_device(slot)
+                self._owner[cid] = 0
 
     # ---- logging (:314-400) ----------------------------------------------------------------------------
     def _log_results(self, resulting_sizes, results, eval, participated, save_raw):
@@ -271,17 +333,45 @@ class FedavgServer(BaseServer):
         else:
             results = [update_client(self.clients[i]) for i in local]
         d = _dist()
-        if d is not None:        # every rank logs the whole round: exchange the (tiny) per-client result dicts
-            gathered = [None] * self.world_size
-            d.all_gather_object(gathered, results)
-            results = [r for part in gathered for r in part]
+        if d is not None:        # every rank logs the whole round: exchange the per-client epoch statistics
+            results = self._exchange_results(d, ids, results)
         sizes = dict(ChainMap(*[r[0] for r in results])) if results else {}
         res = dict(ChainMap(*[r[1] for r in results])) if results else {}
-        sizes = {i: sizes[i] for i in ids}
-        res = {i: res[i] for i in ids}
+        # The reference hands `dict(ChainMap(*results))` on: clients in REVERSED completion order (:578-579).  With
+        # sequential clients that is descending id; worker threads make the order (and, through the stale
+        # `identifier` at :648, the --compensation/modality_exact normaliser) racy there — here it is always the
+        # sequential order, whatever args.num_thread is.
+        sizes = {i: sizes[i] for i in reversed(list(ids))}
+        res = {i: res[i] for i in reversed(list(ids))}
+        self.round_results = res        # {client id: {epoch: {'loss', 'metrics'}}} of this round
         self.results[self.round]["clients_updated"] = self._log_results(sizes, res, eval=False, participated=True,
                                                                         save_raw=False)
         return sizes
+
+    def _exchange_results(self, d, ids, results):
+        """All ranks end with every sampled client's {epoch: {loss, metrics}}: one fixed-size all-reduce of a
+        [clients, E, 3] tensor (each rank fills the rows of the clients it trained) instead of pickled objects."""
+        ids = list(ids)
+        row = {cid: i for i, cid in enumerate(ids)}
+        E = self.args.E
+        t = torch.zeros(len(ids), E, 3, dtype=torch.float64)
+        for _, res in results:
+            for cid, per_epoch in res.items():
+                for e, r in per_epoch.items():
+                    acc = r["metrics"].get("acc1")
+                    t[row[cid], e - 1] = torch.tensor([r["loss"], 0.0 if acc is None else acc, 0.0 if acc is None else 1.0],
+                                                      dtype=torch.float64)
+        t = t.to(self.server_device)
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+        t = t.cpu()
+        out = []
+        for cid in ids:
+            per_epoch = {}
+            for e in range(E):
+                loss, acc, has = t[row[cid], e].tolist()
+                per_epoch[e + 1] = {"loss": loss, "metrics": {"acc1": acc} if has > 0.5 else {}}
+            out.append(({cid: len(self.clients[cid].training_set)}, {cid: per_epoch}))
+        return out
 
     # ---- aggregation (:591-668) --------------------------------------------------------------------------
     def _ctx(self, datasets, in_place=True):
@@ -308,11 +398,14 @@ class FedavgServer(BaseServer):
         gl = self._ctx(datasets)
         cl = self._client_ctx(ids, updated_sizes)
         for c in cl:
-            if c.arena is not None and c.arena.device != self.server_device:
-                raise RuntimeError("aggregation expects client arenas on the server device; run one process per GPU "
-                                   "(torchrun) to use several GPUs")
+            # single process, several GPUs (the reference's thread-per-client mode): the kernel on the server GPU
+            # reads the remote arena in place over NVLink; without a peer path the arena is copied over first.
+            # Either way every value is folded in ascending client id by one launch: bit-exact.
+            if c.arena is not None and c.arena.device != self.server_device and not self._peer_readable(c.arena.device):
+                c.arena = c.arena.to(self.server_device)
         flags = dict(args_modalities=self.args.modalities, share_scope_flag=self.args.share_scope,
-                     compensation=self.args.compensation, with_aux=self.args.with_aux, fedavg=fedavg)
+                     compensation=self.args.compensation, with_aux=self.args.with_aux, fedavg=fedavg,
+                     stale_id=list(updated_sizes.keys())[-1] if len(updated_sizes) else None)
         d = _dist()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.device(self.server_device):

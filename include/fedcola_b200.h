@@ -21,6 +21,12 @@ extern "C" {
 
 #define FC_ABI_VERSION 1
 
+/* return codes of every int-returning entry point */
+#define FC_OK 0
+#define FC_ERR_INVALID (-1)      /* bad argument (validated before touching the device) */
+#define FC_ERR_CUDA (-2)         /* a CUDA runtime / driver call failed; fc_last_error() has the text */
+#define FC_ERR_UNSUPPORTED (-3)  /* combination not built / hardware path absent */
+
 const char* fc_last_error(void);
 int fc_abi_version(void);
 /* number of CUDA kernels this library has launched so far in this process */
@@ -29,6 +35,17 @@ unsigned long long fc_launch_count(void);
  * small problems run many tiles / items per CTA (the regime of the bench shapes).  0 = no cap.  Process-wide;
  * returns the previous value. */
 int fc_set_grid_cap(int max_ctas);
+
+/* Enable peer (NVLink) access from `device` to memory on `peer_device`, so that fc_aggregate launched on `device`
+ * can read client arenas trained on another GPU of the same process in place (ref: the thread-per-client
+ * `cuda:(i % ngpu)` placement, src/server/fedavgserver.py:310-311).  FC_ERR_UNSUPPORTED if there is no peer path. */
+int fc_enable_peer_access(int device, int peer_device);
+
+/* Host -> device gather of one batch: dst[i, :] = src_host[idx[i], :] (row_bytes each) as cudaMemcpyAsync on `stream`,
+ * consecutive indices merged; src_host should be pinned, idx is a HOST array.
+ * ref: src/client/fedavgclient.py:79-84 (DataLoader collation + .to(device) of every batch). */
+int fc_h2d_rows(void* dst, const void* src_host, const long long* idx, int n, long long row_bytes, int device,
+                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Server aggregation                                    ref: src/server/fedavgserver.py:597,656-666

@@ -69,8 +69,10 @@ def reference_server(case, seq_len=16):
     return server, args
 
 
-def reference_aggregate(case):
-    """{dataset: {key: np.ndarray}} after the reference's _aggregate loop (fedavgserver.py:812-819)."""
+def reference_aggregate(case, descending_sizes=False):
+    """{dataset: {key: np.ndarray}} after the reference's _aggregate loop (fedavgserver.py:812-819).
+    descending_sizes: hand `updated_sizes` over in descending-id key order, as `dict(ChainMap(*results))` produces
+    it inside update() when clients complete sequentially (fedavgserver.py:578-579)."""
     import helpers as H
     ref_shim.install()
     import src.server.fedavgserver as fs
@@ -78,6 +80,8 @@ def reference_aggregate(case):
     _, _, _, _, scales, datasets, clients = H.AGG_CASES[case]
     ids = list(range(len(clients)))
     sizes = {cid: n for cid, (_, n) in enumerate(clients)}
+    if descending_sizes:
+        sizes = {cid: sizes[cid] for cid in reversed(ids)}
     out = {}
     for i, ds in enumerate(server.global_models.keys()):
         server.global_model = server.global_models[ds]

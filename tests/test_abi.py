@@ -95,6 +95,51 @@ def test_install_as_src_registers_drop_in_modules():
             assert hasattr(import_module(f"src.server.{alg}server"), f"{alg.title()}Server")
             assert hasattr(import_module(f"src.client.{alg}client"), f"{alg.title()}Client")
             assert hasattr(import_module(f"src.algorithm.{alg}"), f"{alg.title()}Optimizer")
+        # timm.create_model('mome_*') — what FedavgServer._init_model calls (fedavgserver.py:151-155) — lands here
+        import timm
+        from fedcola_b200.harness import make_args
+        from fedcola_b200.models import mome
+        args = make_args(vocab_size=512, seq_len=16)
+        kw = dict(pretrained=False, num_classes=[100, None], modalities=["img", None], args=args, tasks=["cls", None])
+        for name in ("mome_small_patch16", "mome_tiny_patch16", "mome_small_patch16_224_in21k",
+                     "mome_base_patch16_224_ours", "mome_toy_patch16_224"):      # mome.py:924-1033
+            assert name in mome._REGISTRY
+        m = timm.create_model("mome_toy_patch16_224", **kw)
+        assert isinstance(m, mome.ModalityAgnosticTransformer) and m.embed_dim == 4
+        with pytest.raises(RuntimeError, match="Unknown model"):
+            timm.create_model("no_such_model_xyz")
     finally:
         for n in names:
-            sys.modules.pop(n, None)
+            if n != "timm.create_model":
+                sys.modules.pop(n, None)
+        sys.modules.pop("timm", None)
+
+
+def test_mp_flag_is_refused_loudly():
+    """--mp (ProcessPoolExecutor clients, fedavgserver.py:560-562) has no equivalent here: raise, do not ignore."""
+    from fedcola_b200.harness import make_args
+    from fedcola_b200.server.fedavgserver import FedavgServer
+    with pytest.raises(NotImplementedError, match="--mp"):
+        FedavgServer(args=make_args(mp=True), writer=None, server_dataset=(None, {}), client_datasets=[],
+                     model_str="mome_d64_l2")
+
+
+def test_placement_rules():
+    from fedcola_b200 import aggregation as agg
+    from fedcola_b200.arena import MatSpec
+    assert agg.place_clients([0] * 5, 2, "reference") == [0, 1, 0, 1, 0]          # cuda:(i % ngpu), :310-311
+    # BASELINE configs[2]: 6 img + 6 txt + 4 img-txt ViT-S clients over 8 ranks
+    sp = MatSpec(embed_dim=384, depth=12, num_heads=6, modalities=("img", "txt"), num_classes=(None, None),
+                 tasks=("rtv", "rtv"), vocab_size=30522, max_text_len=64)
+    f = {m: agg.train_flops_per_sample(sp, m) for m in ("img", "txt", "img+txt")}
+    assert abs(f["img"] / 27.59e9 - 1) < 0.01 and abs(f["txt"] / 8.38e9 - 1) < 0.01 and abs(f["img+txt"] / 35.97e9 - 1) < 0.01
+    costs = [f["img"]] * 6 + [f["txt"]] * 6 + [f["img+txt"]] * 4
+
+    def spread(rule):
+        slots = agg.place_clients(costs, 8, rule)
+        load = [sum(c for c, s in zip(costs, slots) if s == r) for r in range(8)]
+        return max(load) / (sum(load) / 8)
+    assert spread("balanced") < spread("reference") and spread("balanced") < 1.35
+    assert agg.place_clients(costs, 8, "balanced") == agg.place_clients(costs, 8, "balanced")   # deterministic
+    with pytest.raises(ValueError):
+        agg.place_clients(costs, 8, "nope")

@@ -102,6 +102,39 @@ def test_random_configuration_against_the_live_reference(seed):
         del H.AGG_CASES[name]
 
 
+@pytest.mark.parametrize("case", ["modality_exact_comp", "fedcola_attn_modality_comp_aux"])
+def test_stale_identifier_follows_the_order_of_updated_sizes(case):
+    """fedavgserver.py:648 reads the loop variable `identifier` after its loop: the LAST key of `updated_sizes`.
+    Inside update() that dict is dict(ChainMap(*results)) — descending id when clients complete sequentially — so
+    the --compensation/modality_exact normaliser there differs from a direct _aggregate(ascending dict) call.
+    The planner takes the key explicitly (`stale_id`); both orders must match the live reference bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import make_golden
+    from fedcola_b200 import aggregation as agg
+    import helpers as H
+    results = {}
+    for descending in (False, True):
+        ref = make_golden.reference_aggregate(case, descending_sizes=descending)
+        gl, cl, scope, flags = H.build_agg_case(case)
+        stale = min(c.id for c in cl) if descending else max(c.id for c in cl)
+        H.run_plan_numpy(agg.AggregationPlan(gl, cl, scope, mode=agg.LERP, stale_id=stale, **flags))
+        for g in gl:
+            got = H.state_dict_of(g.spec, g.arena_out.numpy())
+            for k in g.spec.required_keys():
+                assert np.array_equal(got[k], ref[g.dataset][k]), (case, descending, g.dataset, k)
+        results[descending] = ref
+    if case == "modality_exact_comp":      # the quirk is observable here: img client first, img+txt client last
+        assert any(not np.array_equal(results[False][ds][k], results[True][ds][k])
+                   for ds in results[False] for k in results[False][ds])
+
+
+def test_update_flow_hands_sizes_over_in_chainmap_order():
+    """dict(ChainMap(*maps)) lists the maps in reverse: the order FedavgServer._request rebuilds (sequential flow)."""
+    from collections import ChainMap
+    maps = [{0: 16}, {3: 24}, {7: 16}]                      # completion order of sequential clients
+    assert list(dict(ChainMap(*maps)).keys()) == [7, 3, 0]
+
+
 def test_client_sampling_matches_the_live_reference():
     """A11: FedavgServer._sample_clients (fedavgserver.py:282-312) — same ids AND same random-state consumption for
     both sampling modes, the evaluation (exclude) branch and the warm-up modality filter."""
@@ -128,13 +161,16 @@ def test_client_sampling_matches_the_live_reference():
 
         def fake():
             clients = [NS(id=i, dataset=d, modality=mod[d], device=None) for i, d in enumerate(client_ds)]
-            return NS(args=args, clients=clients, Cs=Cs, round=rnd, world_size=2, _client_device=lambda i: "cuda:0")
+            return NS(args=args, clients=clients, Cs=Cs, round=rnd, world_size=2, server_device="cuda:0",
+                      _client_devices=["cuda:0"], _place=lambda ids: our_fs.FedavgServer._place(me[0], ids))
 
         random.seed(seed)
+        me = [None]
         want = ref_fs.FedavgServer._sample_clients(fake(), exclude=list(exclude))
         state_ref = random.getstate()
         random.seed(seed)
-        mine = fake()
+        me = [None]
+        mine = me[0] = fake()
         got = our_fs.FedavgServer._sample_clients(mine, exclude=list(exclude))
         assert got == want, (trial, vars(args), exclude)
         assert random.getstate() == state_ref
