@@ -328,7 +328,7 @@ def run_ours(a):
     #      the reference's own run of the same sample on the host cores (same seed -> bit-identical initial weights)
     parity = None
     n_sample = a.ref_samples or cfg["B"]
-    if a.parity and rank == 0:
+    if a.parity and n_gpus == 1:      # (N=1 arm only: the comparators below run there)
         pargs, pspecs = sample_workload(cfg, n_sample, data_resident="device", server_device=str(dev), num_thread=1,
                                         client_devices=[str(dev)], precision=a.precision)
         srv, _ = make_server("device", pargs, pspecs)

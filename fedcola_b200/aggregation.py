@@ -166,7 +166,9 @@ class AggregationPlan:
         if mode == LERP and any(c.arena is None for c in clients):
             raise ValueError("sequential-lerp aggregation needs every sampled client's arena on this GPU; "
                              "use mode=WSUM for clients sharded across ranks")
-        sig = (mode, bool(fedavg), bool(include_global_term), stale_id, tuple(args_modalities), share_scope_flag,
+        # (the tables depend on client ids only through their order: key the stale identifier by its position)
+        stale_pos = None if stale_id is None else [c.id for c in clients].index(stale_id)
+        sig = (mode, bool(fedavg), bool(include_global_term), stale_pos, tuple(args_modalities), share_scope_flag,
                bool(compensation), bool(with_aux), id(param_scope), len(param_scope),
                tuple((g.spec.signature, g.dataset, g.modality, g.task, g.out_modality_scale, g.out_offset_of is not None)
                      for g in globals_),
