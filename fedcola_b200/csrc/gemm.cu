@@ -46,15 +46,19 @@ constexpr int EPI_BUF_BYTES = 32 * 128;    // per epilogue warp: 32 rows x 128 B
 constexpr int EPI_BIAS_BYTES = 64 * 4;      // per epilogue warp: the bias of the chunk's (up to) 64 columns
 constexpr int TMEM_BUF_COLS = 256;         // two accumulator buffers at columns 0 and 256
 
-template <int BN, int EPI> struct Cfg {
+template <int BN, int EPI, int PAIR> struct Cfg {
   static constexpr int EPI_WARPS = epi_warps_for(EPI);
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * (EPI_BUF_BYTES + EPI_BIAS_BYTES);
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // what fits beside the epilogue staging
-  static constexpr int STAGES = EPI_WARPS == 8 ? (BN == 128 ? 5 : 4) : (BN == 128 ? 4 : 3);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 512 /*barriers*/;
+  // pair mode (cta_group::2): a stage holds this CTA's 128 rows of A and HALF of the B tile (BN/2 rows / columns)
+  static constexpr int STAGE_BYTES = A_BYTES + (PAIR ? B_BYTES / 2 : B_BYTES);
+  // as many ring stages as fit beside the epilogue staging (1 KB of barriers / slack), at most 8
+  static constexpr int FIT = (232448 - EPI_STAGE_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*barriers*/;
+  static_assert(STAGES >= 3, "too few pipeline stages");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+  static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 16 <= 1024, "barrier block");
 };
 
 struct GemmParams {
@@ -75,6 +79,29 @@ struct GemmParams {
   int patches;              // EPI_PATCH: P (196)
   float alpha;
   int debug;                // measurement aid (FC_GEMM_DEBUG env): 1 = skip epilogue work, 2 = skip TMA+MMA work
+  int pair;                 // 1: CTA pairs (cta_group::2) compute 256 x BN tiles, each CTA stages its 128 rows of A and half of B
+};
+
+// Persistent tile walk.  pair == 0: tile t = blockIdx.x, +gridDim.x, ... -> (split, m_blk, n_blk), n fastest.
+// pair == 1: the CTA pair (blockIdx.x >> 1) walks pair-tiles (split, m_pair, n_blk); rank r owns m_blk = 2*m_pair + r
+// (an M tile past the matrix is all TMA zero fill / clipped stores).
+template <int PAIR> struct TileWalk {
+  int first, step, total, tiles_mn, n_tiles, rank;
+  __device__ TileWalk(const GemmParams& p) {
+    rank = PAIR ? static_cast<int>(blockIdx.x & 1) : 0;
+    first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    n_tiles = p.n_tiles;
+    tiles_mn = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+    total = tiles_mn * p.splits;
+  }
+  __device__ void decode(int tile, int& split, int& m_blk, int& n_blk) const {
+    split = tile / tiles_mn;
+    const int mn = tile - split * tiles_mn;
+    const int mq = mn / n_tiles;
+    n_blk = mn - mq * n_tiles;
+    m_blk = PAIR ? 2 * mq + rank : mq;
+  }
 };
 
 // Exact-erf GELU (nn.GELU() default) evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf
@@ -409,13 +436,15 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
 //   tile -> (split, m_blk, n_blk), n fastest so CTAs running side by side share the A rows in L2.
 // smem ring (TMA -> MMA) runs across tile boundaries; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int PAIR>
 __global__ void __launch_bounds__(gemm_threads_for(EPI), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                  const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using C = Cfg<BN, EPI>;
+  using C = Cfg<BN, EPI, PAIR>;
   constexpr int STAGES = C::STAGES;
+  constexpr bool pair = PAIR != 0;
+  constexpr int stage_bytes = C::STAGE_BYTES;
   constexpr int EPI_WARPS = C::EPI_WARPS;
   constexpr int EPI_STAGE_BYTES = C::EPI_STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
@@ -430,8 +459,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_mn * p.splits;
+  const TileWalk<PAIR> walk(p);
+  // pair mode: both CTAs use the same stage offsets; the leader's MMAs read A and B from both shared memories.
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -448,70 +477,98 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full_bar[b], 1);
-        mbar_init(&tmem_empty_bar[b], EPI_WARPS);    // one arrival per epilogue warp
+        mbar_init(&tmem_empty_bar[b], pair ? 2 * EPI_WARPS : EPI_WARPS);    // one arrival per epilogue warp (of both CTAs)
       }
       for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&epi_bar[w], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (pair) {
+      tmem_alloc_pair(tmem_slot, 512);
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();           // the peer's barriers and TMEM exist before anything crosses CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && !(p.debug & 2)) {
+    if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn, mn = tile - split * tiles_mn;
-        const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+      for (int tile = walk.first; tile < walk.total; tile += walk.step) {
+        int split, m_blk, n_blk;
+        walk.decode(tile, split, m_blk, n_blk);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = (p.debug & 2) ? kb1 : kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          uint8_t* a_dst = smem + s * C::STAGE_BYTES;
+          uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + A_BYTES;
-          if (A_MN) {   // [K, M] global: boxes {64 (m), 64 (k)}
-            tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
-            tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
-          } else {      // [M, K] global: box {64 (k), 128 (m)}
-            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-          }
-          if (B_MN) {
+          if constexpr (pair) {
+            // Both CTAs' loads complete their bytes on the LEADER's full barrier (its MMA warp is the only consumer);
+            // the leader alone arms it, with the bytes of both — a local arrive: no cluster-scope release in this loop.
+            // (The peer's bytes may land before the leader arms the phase: the transaction count just goes negative;
+            //  they cannot run a phase ahead, because the peer's slot is only freed by the commit of this phase's MMAs.)
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (walk.rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            if (A_MN) {
+              tma_load_2d_pair(a_dst, &tmA, lbar, m0, kb * BK);
+              tma_load_2d_pair(a_dst + 8192, &tmA, lbar, m0 + 64, kb * BK);
+            } else {
+              tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
+            }
+            const int nh = n0 + walk.rank * (BN / 2);          // this CTA's half of the B tile
+            if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
-          } else {      // box {64 (k), BN (n)}
-            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(b_dst + j * 8192, &tmB, lbar, nh + j * 64, kb * BK);
+            } else {      // box {64 (k), BN/2 (n)}
+              tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, nh);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            if (A_MN) {   // [K, M] global: boxes {64 (m), 64 (k)}
+              tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
+              tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
+            } else {      // [M, K] global: box {64 (k), 128 (m)}
+              tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+            } else {      // box {64 (k), BN (n)}
+              tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && !(pair && walk.rank != 0)) {     // pair mode: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(pair ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int split = tile / tiles_mn;
+      for (int tile = walk.first; tile < walk.total; tile += walk.step, ++it) {
+        const int split = tile / walk.tiles_mn;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const int buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_COLS;
-        if (p.debug & 2) {                     // measurement aid: no operands, no MMAs — epilogue-only timing
+        if ((p.debug & 2) && !pair) {          // measurement aid: no operands, no MMAs — epilogue-only timing
           mbar_arrive(&tmem_full_bar[buf]);
           continue;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -521,12 +578,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                      : umma_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (pair) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
+          if constexpr (pair) umma_commit_pair(&empty_bar[s]);   // slot free in both CTAs once these MMAs retire
+          else umma_commit(&empty_bar[s]);     // smem slot free once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full_bar[buf]);      // accumulator complete
+        if constexpr (pair) umma_commit_pair(&tmem_full_bar[buf]);   // accumulator halves complete in both CTAs
+        else umma_commit(&tmem_full_bar[buf]); // accumulator complete
       }
     }
   } else {
@@ -540,9 +600,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t eph = 0;
     constexpr int CW = EPI == FC_EPI_PATCH ? 32 : EpiTraits<EPI>::kCW;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int mn = tile % tiles_mn;
-      const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+    // pair mode: the accumulator is released to the LEADER's MMA warp by the epilogue warps of both CTAs
+    uint32_t leader_empty[2] = {0u, 0u};
+    if constexpr (pair) {
+      leader_empty[0] = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+      leader_empty[1] = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    }
+    auto release_acc = [&](int b) {
+      if constexpr (pair) mbar_arrive_cluster(leader_empty[b]);
+      else mbar_arrive(&tmem_empty_bar[b]);
+    };
+    for (int tile = walk.first; tile < walk.total; tile += walk.step, ++it) {
+      int split_unused, m_blk, n_blk;
+      walk.decode(tile, split_unused, m_blk, n_blk);
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int buf_i = it & 1;
       mbar_wait(&tmem_full_bar[buf_i], (it >> 1) & 1);
       tc_fence_after();
@@ -555,7 +626,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (n0 + c * CW < p.N) last_c = c;
       if (last_c < 0 || (p.debug & 1)) {       // nothing to read in this tile (or main-loop-only timing)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
+        if (lane == 0) release_acc(buf_i);
         continue;
       }
 #pragma unroll 1
@@ -573,7 +644,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == last_c) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
+            if (lane == 0) release_acc(buf_i);
           }
           if (lane < 16) {
 #pragma unroll
@@ -616,7 +687,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == last_c) {                   // last TMEM read of this tile by this warp: hand the buffer back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf_i]);
+            if (lane == 0) release_acc(buf_i);
           }
           if (p.bias != nullptr) {             // ... and shares it with the other lanes through shared memory
             if (2 * lane < CW)
@@ -630,9 +701,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) tma_store_wait_all();       // all bulk stores of this warp are globally complete before exit
   }
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();            // the peer may still read this CTA's smem / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -678,15 +751,24 @@ int g_prof_on = 0;
 
 struct EpiMaps { CUtensorMap o, o2, r; };
 
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int device,
            cudaStream_t st) {
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
-  FC_SMEM_OPT_IN(kern, (Cfg<BN, EPI>::SMEM_BYTES));
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  using C = Cfg<BN, EPI, PAIR>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, PAIR>;
+  FC_SMEM_OPT_IN(kern, (C::SMEM_BYTES));
   int grid = fc_num_sms(device);
-  if (grid > total_tiles) grid = total_tiles;
-  grid = fc_apply_grid_cap(grid);
+  if (PAIR) {
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+    grid &= ~1;
+    if (grid > 2 * pair_tiles) grid = 2 * pair_tiles;
+    grid = fc_apply_grid_cap(grid) & ~1;
+    if (grid < 2) grid = 2;
+  } else {
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    if (grid > total_tiles) grid = total_tiles;
+    grid = fc_apply_grid_cap(grid);
+  }
   ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K};
   const bool prof = __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) != 0;
   if (prof) {
@@ -694,7 +776,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
     cudaEventCreate(&rec.b);
     cudaEventRecord(rec.a, st);
   }
-  kern<<<grid, gemm_threads_for(EPI), Cfg<BN, EPI>::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
+  if (PAIR) {       // CTA pairs: clusters of two along x (cta_group::2 pairs rank r with r ^ 1)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(gemm_threads_for(EPI));
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.o, em.o2, em.r, p));
+  } else {
+    kern<<<grid, gemm_threads_for(EPI), C::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
+  }
   if (prof) {
     cudaEventRecord(rec.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -709,15 +807,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
 //   dX       A K-major, B MN    : BF16, MULAUX, F32
 //   dW       A,B MN-major       : ATOMIC_F32, F32
 //   (A MN, B K)                 : F32 (parity tests)
-template <int BN>
+// each as a single-CTA kernel (128 x BN tiles) and — except PATCH, and BN = 192 with an MN-major B whose half tile is
+// not a whole number of 64-column blocks — as a CTA-pair kernel (cta_group::2, 256 x BN tiles).
+template <int BN, int PAIR>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int a_mn, int b_mn,
               int device, cudaStream_t st) {
 #define FC_CASE(AM, BMJ, E) \
-  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E>(ta, tb, em, p, device, st)
+  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E, PAIR>(ta, tb, em, p, device, st)
   FC_CASE(0, 0, FC_EPI_BF16); FC_CASE(0, 0, FC_EPI_GELU); FC_CASE(0, 0, FC_EPI_RESID); FC_CASE(0, 0, FC_EPI_F32);
-  FC_CASE(0, 0, FC_EPI_PATCH);
-  FC_CASE(0, 1, FC_EPI_BF16); FC_CASE(0, 1, FC_EPI_MULAUX); FC_CASE(0, 1, FC_EPI_F32);
-  FC_CASE(1, 1, FC_EPI_ATOMIC_F32); FC_CASE(1, 1, FC_EPI_F32);
+  if constexpr (!PAIR) { FC_CASE(0, 0, FC_EPI_PATCH); }
+  if constexpr (!PAIR || BN % 128 == 0) {
+    FC_CASE(0, 1, FC_EPI_BF16); FC_CASE(0, 1, FC_EPI_MULAUX); FC_CASE(0, 1, FC_EPI_F32);
+    FC_CASE(1, 1, FC_EPI_ATOMIC_F32); FC_CASE(1, 1, FC_EPI_F32);
+  }
   FC_CASE(1, 0, FC_EPI_F32);
 #undef FC_CASE
   FC_FAIL(FC_ERR_UNSUPPORTED, "fc_gemm_bf16: epilogue %d is not built for operand majors (a_mn=%d, b_mn=%d)", p.epi,
@@ -817,13 +919,23 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   {
     static const int dbg = getenv("FC_GEMM_DEBUG") ? atoi(getenv("FC_GEMM_DEBUG")) : 0;
     p.debug = dbg;
+    // Experiment knobs: FC_GEMM_BN forces the tile width; FC_GEMM_PAIR = 0 never / 1 whenever legal: CTA pairs
+    // (cta_group::2, 256 x BN pair tiles).  Legal: not the PATCH epilogue; an MN-major B needs BN % 128 == 0 (each
+    // CTA's half tile must be whole 64-column blocks).
+    static const int force_bn = getenv("FC_GEMM_BN") ? atoi(getenv("FC_GEMM_BN")) : 0;
+    static const int use_pairs = getenv("FC_GEMM_PAIR") ? atoi(getenv("FC_GEMM_PAIR")) : 0;
+    if (force_bn == 128 || force_bn == 192 || force_bn == 256) {
+      bn = force_bn;
+      p.n_tiles = (N + bn - 1) / bn;
+    }
+    p.pair = (use_pairs && epi != FC_EPI_PATCH && (!b_mn_major || bn % 128 == 0) && !(p.debug & 2)) ? 1 : 0;
   }
   CUtensorMap ta, tb;
   int rc;
   // K-major operand: global [rows, K]; MN-major operand: global [K, rows].
   rc = a_mn_major ? make_tmap(&ta, A, K, M, lda, 64, 64) : make_tmap(&ta, A, M, K, lda, 64, BM);
   if (rc) return rc;
-  rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, bn);
+  rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, p.pair ? bn / 2 : bn);
   if (rc) return rc;
   // epilogue tiles: 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), stored / reduced / loaded by TMA
   EpiMaps em;
@@ -848,7 +960,13 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_bn<256>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
-  if (bn == 192) return launch_bn<192>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
-  return launch_bn<128>(ta, tb, em, p, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, device, st);
+  const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
+  if (p.pair) {
+    if (bn == 256) return launch_bn<256, 1>(ta, tb, em, p, am, bm, device, st);
+    if (bn == 192) return launch_bn<192, 1>(ta, tb, em, p, am, bm, device, st);
+    return launch_bn<128, 1>(ta, tb, em, p, am, bm, device, st);
+  }
+  if (bn == 256) return launch_bn<256, 0>(ta, tb, em, p, am, bm, device, st);
+  if (bn == 192) return launch_bn<192, 0>(ta, tb, em, p, am, bm, device, st);
+  return launch_bn<128, 0>(ta, tb, em, p, am, bm, device, st);
 }
