@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-gpu-eager", dest="gpu_eager", action="store_false")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
+    ap.add_argument("--client-group", type=int, default=int(os.environ.get("FC_CLIENT_GROUP", 3)),
+                    help="clients of one architecture trained in lockstep by shared kernel launches (1 = off)")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference arms: samples per client per step (0 = one batch)")
     ap.add_argument("--ref-budget-s", type=float, default=180.0, help="reference arm: stop timing new steps after this long")
@@ -266,7 +268,8 @@ def run_ours(a):
         # world_size 1: clients stay on THIS GPU even when the node has more (the reference's own multi-GPU mode —
         # one process, clients on cuda:(i % ngpu) — is exercised by tests/test_multigpu_gpu.py, not timed here)
         args = args or workload_args(cfg, counts, data_resident=resident, server_device=str(dev), num_thread=a.threads,
-                                     client_devices=[str(dev)], placement=a.placement, precision=a.precision)
+                                     client_devices=[str(dev)], placement=a.placement, precision=a.precision,
+                                     client_group=a.client_group)
         random.seed(args.seed)
         torch.manual_seed(args.seed)
         cds = make_client_datasets(specs or client_specs(cfg, counts), seq_len=SEQ, share=True)
@@ -330,7 +333,7 @@ def run_ours(a):
     n_sample = a.ref_samples or cfg["B"]
     if a.parity and n_gpus == 1:      # (N=1 arm only: the comparators below run there)
         pargs, pspecs = sample_workload(cfg, n_sample, data_resident="device", server_device=str(dev), num_thread=1,
-                                        client_devices=[str(dev)], precision=a.precision)
+                                        client_devices=[str(dev)], precision=a.precision, client_group=a.client_group)
         srv, _ = make_server("device", pargs, pspecs)
         srv.round = 1
         ids = srv.update()
@@ -409,8 +412,9 @@ def run_ours(a):
                        "precision": ("bf16 operands / fp32 accumulate" if a.precision == "bf16" else
                                      "fp32-accurate split-operand mode") + ", fp32 master weights+optimizer+aggregation",
                        "l2": "inputs larger than L2 (GBs of activations and parameters per round)",
-                       "parallelism": f"clients sharded over {n_gpus} GPU(s) ({a.placement} placement); {a.threads} client "
-                                      f"worker thread(s)/GPU (args.num_thread), each on its own CUDA stream"},
+                       "parallelism": f"clients sharded over {n_gpus} GPU(s) ({a.placement} placement); lockstep groups of <= "
+                                      f"{a.client_group} same-architecture clients share their kernel launches; {a.threads} "
+                                      f"worker thread(s)/GPU (args.num_thread), one group at a time each, on its own CUDA stream"},
             "gpu_launches": launches_timed,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(gemm_tflops, 2),

@@ -130,6 +130,75 @@ class _ClientData:
         side.synchronize()
 
 
+LOSS_KIND = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}
+
+
+def update_group(clients):
+    """Local training of a LOCKSTEP GROUP of clients: `FedavgClient.update()` (fedavgclient.py:55-116) for every client
+    of the group, with batch s of all of them trained by ONE native call (runtime.group_step -> fc_client_step_group:
+    every GEMM / attention / LayerNorm launch covers the whole group).  The reference trains the same clients side by
+    side in ThreadPoolExecutor workers (fedavgserver.py:566-577); on a B200 one ViT-S client at B=112 does not fill the
+    machine — 40-50 % of a GEMM launch is fixed cost — so clients of one architecture share their launches instead.
+
+    The clients must sit on one device and hold the same model architecture (the server groups them by dataset);
+    batch counts and sizes may differ (a client with fewer batches drops out of the later steps; a short last batch
+    is trained in its own call).  Returns {client id: {epoch: {'loss', 'metrics'}}}."""
+    c0 = clients[0]
+    dev = torch.device(c0.device)
+    E = c0.args.E
+    for c in clients:
+        if torch.device(c.device) != dev or c.model.spec.signature != c0.model.spec.signature:
+            raise ValueError("clients of a lockstep group must share the device and the model architecture")
+    results = {c.id: {} for c in clients}
+    with torch.cuda.device(dev):
+        for c in clients:
+            c._begin_update(dev)
+        # every client's batches for all its epochs, drawn client by client: the order in which sequential clients
+        # (--num_thread 1) consume the global torch RNG in the reference
+        plan = {}
+        for c in clients:
+            plan[c.id] = [epoch_batches(c._index_loader) for _ in range(E)]
+            if c.args.debug:
+                plan[c.id] = [b[:2] for b in plan[c.id]]
+        rng_mode = getattr(c0.args, "droppath_rng", "fused")
+        for e in range(E):
+            feeds = {c.id: iter(c._staged.feed(plan[c.id][e])) for c in clients}
+            seen = {c.id: 0 for c in clients}
+            for c in clients:
+                c.trainer.stats.zero_()
+            for s in range(max(len(plan[c.id][e]) for c in clients)):
+                buckets = {}                      # batch size -> clients that have a batch of that size at step s
+                for c in clients:
+                    if s < len(plan[c.id][e]):
+                        buckets.setdefault(len(plan[c.id][e][s]), []).append(c)
+                for n, members in buckets.items():
+                    for k in range(0, len(members), R.MAX_GROUP):
+                        part = members[k:k + R.MAX_GROUP]
+                        for c in part:
+                            a, b = next(feeds[c.id])
+                            dp = R.droppath_scales(c.model.spec, n, dev, True, rng_mode)
+                            if c.modality == "img":
+                                c.trainer.prepare(a, None, b, LOSS_KIND["img"], dp)
+                            elif c.modality == "txt":
+                                c.trainer.prepare(None, a, b, LOSS_KIND["txt"], dp)
+                            else:
+                                c.trainer.prepare(a, b, None, LOSS_KIND["img+txt"], dp)
+                            seen[c.id] += n
+                        R.group_step([c.trainer for c in part])
+            for c in clients:
+                stats = c.trainer.stats.tolist()                 # ONE device->host read per client and epoch
+                num = len(plan[c.id][e])
+                total = num * c.args.B if (c.args.debug and num >= 2) else len(c.training_set)
+                res = {"loss": stats[2] / total, "metrics": {}}
+                if c.modality != "img+txt":
+                    res["metrics"] = {name: stats[1] / max(seen[c.id], 1) for name in c.eval_metrics if name == "acc1"}
+                results[c.id][e + 1] = res
+                logger.info(f"[Client {c.id}] loss: {res['loss']}" +
+                            (f", acc1: {res['metrics'].get('acc1')}" if c.modality != "img+txt" else ""))
+            del feeds
+    return results
+
+
 class FedavgClient(BaseClient):
     def __init__(self, args, training_set, test_set, task="cls", eval_metrics=["acc1"], modality="ct", writer=None,
                  criterion="CrossEntropyLoss"):
@@ -178,7 +247,12 @@ class FedavgClient(BaseClient):
                                max_grad_norm=self.args.max_grad_norm, prox_mu=mu, global_arena=global_arena)
 
     def update(self):
-        dev = torch.device(self.device)
+        """Local training of this client alone (fedavgclient.py:55-116) — a lockstep group of one."""
+        return update_group([self])[self.id]
+
+    def _begin_update(self, dev):
+        """Everything update() does before its epoch loop (:56-63): model to the device in train mode, data handle,
+        a fresh optimizer (moments never persist across rounds)."""
         if dev.type != "cuda":
             raise RuntimeError("fedcola_b200: clients train on a CUDA device; there is no CPU path "
                                f"(client.device = {self.device!r})")
@@ -194,39 +268,9 @@ class FedavgClient(BaseClient):
         if (resident, str(dev)) not in cache:
             cache[(resident, str(dev))] = _ClientData(self.training_set, self.modality, resident, dev,
                                                       cache_items=getattr(self.args, "cache_dataset", False))
-        data = self._staged = cache[(resident, str(dev))]
-        with torch.cuda.device(dev):
-            trainer = self.trainer = self._make_trainer()        # fresh optimizer state every round (:63)
-            spec = self.model.spec
-            kind = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}[self.modality]
-            rng_mode = getattr(self.args, "droppath_rng", "fused")
-            results = {}
-            logger.info(f"[{self.task.upper()}] [{self.modality.upper()}] ...working on client {self.id}... ")
-            for e in range(self.args.E):
-                trainer.stats.zero_()
-                num = seen = 0
-                batches = epoch_batches(self._index_loader)     # the reference's DataLoader draws, exactly
-                if self.args.debug:
-                    batches = batches[:2]
-                for idx, (a, b) in zip(batches, data.feed(batches)):
-                    dp = R.droppath_scales(spec, len(idx), dev, True, rng_mode)
-                    if self.modality == "img":
-                        trainer.step(a, None, b, kind, dp)
-                    elif self.modality == "txt":
-                        trainer.step(None, a, b, kind, dp)
-                    else:
-                        trainer.step(a, b, None, kind, dp)
-                    num += 1
-                    seen += len(idx)
-                stats = trainer.stats.tolist()                   # ONE device->host read per epoch
-                total = num * self.args.B if (self.args.debug and num >= 2) else len(self.training_set)
-                res = {"loss": stats[2] / total, "metrics": {}}
-                if self.modality != "img+txt":
-                    res["metrics"] = {name: stats[1] / max(seen, 1) for name in self.eval_metrics if name == "acc1"}
-                results[e + 1] = res
-                logger.info(f"[Client {self.id}] loss: {res['loss']}" +
-                            (f", acc1: {res['metrics'].get('acc1')}" if self.modality != "img+txt" else ""))
-        return results
+        self._staged = cache[(resident, str(dev))]
+        self.trainer = self._make_trainer()
+        logger.info(f"[{self.task.upper()}] [{self.modality.upper()}] ...working on client {self.id}... ")
 
     @torch.inference_mode()
     def evaluate(self):

@@ -94,8 +94,16 @@ __device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_des
 // operands with one 64-bit add instead of rebuilding the descriptor (the single issuing thread is a bottleneck).
 __device__ __forceinline__ uint64_t desc_at(uint64_t zero_addr_desc, uint32_t addr) { return zero_addr_desc + (addr >> 4); }
 
+// Client groups (FC_ATTN_MAX_GROUPS): one launch walks the (sample, head) items of several clients' qkv tensors of the
+// same shape — item = (group, sample, head) — so the persistent kernel's fixed costs are paid once per client group.
+constexpr int MAXG = FC_ATTN_MAX_GROUPS;
 struct FwdMaps {
   CUtensorMap qkv_a, qkv_b;                  // box rows RA (first 128-token tile) / RB (remainder tile)
+};
+struct FwdGroups {
+  FwdMaps maps[MAXG];
+  __nv_bfloat16* out[MAXG];
+  float* lse[MAXG];
 };
 
 // Persistent: CTA c handles (sample, head) items c, c+grid, ...  Warp 16 is the control warp: its lane 0 prefetches
@@ -103,8 +111,8 @@ struct FwdMaps {
 // output.  S accumulators are double-buffered in TMEM (columns 0 / 256) and O overlays its own consumed S, so
 // QK^T of tile T+1 and P·V of tile T run under the softmax warps' work on the neighbouring tiles.
 __global__ void __launch_bounds__(kFwdThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
-                   int n_items, int N, int H, int nbuf, float scale_log2e) {
+attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_per_group, int N, int H, int nbuf,
+                   float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
 #ifdef FC_ATTN_PROF
   __shared__ long long prof_s[16 * 12];
@@ -152,14 +160,18 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
   if (warp == kSoftmaxWarps) {
     // ================= control warp: TMA producer + MMA issuer (one lane) =================
     if (lane == 0 && n_my > 0) {
-      prefetch_tmap(&maps.qkv_a);
-      prefetch_tmap(&maps.qkv_b);
+      for (int g = 0; g * items_per_group < n_items; ++g) {
+        prefetch_tmap(&G.maps[g].qkv_a);
+        prefetch_tmap(&G.maps[g].qkv_b);
+      }
       const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       auto buf_addr = [&](int k) { return smem_u32(smem) + (k % nbuf) * buf_bytes; };
       auto issue_load = [&](int k) {
         const int item = first + k * stride;
-        const int b = item / H, h = item % H;
+        const int grp = item / items_per_group, rem = item - grp * items_per_group;
+        const int b = rem / H, h = rem % H;
+        const FwdMaps& maps = G.maps[grp];
         uint8_t* base = smem + (k % nbuf) * buf_bytes;
         uint64_t* bar = &tma_bar[k % nbuf];
         mbar_arrive_expect_tx(bar, buf_bytes);
@@ -242,10 +254,10 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = pack2(f[2 * i] * inv, f[2 * i + 1] * inv);
     };
-    auto store_o = [&](const uint32_t (&o)[8], int bh_row0, int h, int qt) {
+    auto store_o = [&](const uint32_t (&o)[8], int bh_row0, int h, int qt, int cg) {
       const int qrow = qt * 128 + row;
       if (qrow < N) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(bh_row0) + qrow) * d + h * HD + grp * 16);
+        uint4* dst = reinterpret_cast<uint4*>(G.out[cg] + (static_cast<size_t>(bh_row0) + qrow) * d + h * HD + grp * 16);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
@@ -257,19 +269,21 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
     };
     const float sc = scale_log2e;
     // row sums of the previous tile -> 1/sum for its O rows, LSE for the backward
-    auto finish_sums = [&](int T, float mb, int bh, int qt) -> float {
+    auto finish_sums = [&](int T, float mb, int bh, int qt, int cg) -> float {     // bh: item index inside its client group
       const uint32_t rd = red_sum_rd + (T & 1) * 2048;
       const float sum = (ld_shared_f32(rd) + ld_shared_f32(rd + 512)) + (ld_shared_f32(rd + 1024) + ld_shared_f32(rd + 1536));
       const int qrow = qt * 128 + row;
+      float* lse_out = G.lse[cg];
       if (grp == 0 && lse_out != nullptr && qrow < N)
         lse_out[static_cast<size_t>(bh) * N + qrow] = 0.69314718056f * (mb + lg2(sum));
       return rcp(sum);
     };
-    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0;
+    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0, prev_cg = 0;
     float prev_mb = 0.f;
     const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;   // item / H == (item * magic) >> 32 for item < 2^16
     for (int k = 0, item = first; k < n_my; ++k, item += stride) {
-      const int b = static_cast<int>((static_cast<unsigned long long>(item) * h_magic) >> 32), h = item - b * H;
+      const int cg = item / items_per_group, rem = item - cg * items_per_group;
+      const int b = static_cast<int>((static_cast<unsigned long long>(rem) * h_magic) >> 32), h = rem - b * H;
       for (int qt = 0; qt < q_tiles; ++qt, ++T) {
         const int sb = depth == 2 ? (T & 1) : 0;
         const uint32_t tS = tmem + sb * s_stride;
@@ -303,7 +317,7 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
         const float mb = mx * sc, nmb = -mb;
         // the previous tile's P·V ran under the work above: fetch its O now (this also frees the P tile)
         uint32_t o[8];
-        if (T > 0) load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
+        if (T > 0) load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt, prev_cg), o);
         PROF(4);
         // ---- pass 2: p = exp2(s*c - max*c) -> bf16 -> swizzled K-major P tile (column block = grp); row sum ----
         // P is left un-normalised (0 < p <= 1); the row of O is scaled by 1/sum in its epilogue.
@@ -339,20 +353,21 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdMaps maps, __nv_bfloat16* __restri
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
         PROF(5);
-        if (T > 0) store_o(o, prev_row0, prev_h, prev_qt);
+        if (T > 0) store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
         prev_mb = mb;
         prev_row0 = b * N;
-        prev_bh = item;
+        prev_bh = rem;
         prev_h = h;
         prev_qt = qt;
+        prev_cg = cg;
         PROF(6);
       }
     }
     if (T > 0) {
       softmax_warps_sync();                   // last tile's row sums
       uint32_t o[8];
-      load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt), o);
-      store_o(o, prev_row0, prev_h, prev_qt);
+      load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt, prev_cg), o);
+      store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
     }
   }
   tc_fence_before();
@@ -387,12 +402,17 @@ constexpr int kRing = 4;                   // dS^T tiles (64 queries each): two 
 struct BwdMaps {
   CUtensorMap qkv_a, qkv_b, do_a, do_b;      // box rows RA / RB
 };
+struct BwdGroups {
+  BwdMaps maps[MAXG];
+  const __nv_bfloat16* o[MAXG];
+  const __nv_bfloat16* d_o[MAXG];
+  const float* lse[MAXG];
+  __nv_bfloat16* dqkv[MAXG];
+  float* dbias[MAXG];
+};
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __restrict__ o_g,
-                   const __nv_bfloat16* __restrict__ do_g, const float* __restrict__ lse_g,
-                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_items, int N, int H,
-                   float scale) {
+attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_per_group, int N, int H, float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   const int RA = N > 128 ? 128 : ((N + 15) & ~15);
@@ -439,23 +459,30 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
   const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;
-  auto item_bh = [&](int item, int& b, int& h) {
-    b = static_cast<int>((static_cast<unsigned long long>(item) * h_magic) >> 32);
-    h = item - b * H;
+  // item -> (client group, sample, head)
+  auto item_bh = [&](int item, int& cg, int& b, int& h) {
+    cg = item / items_per_group;
+    const int rem = item - cg * items_per_group;
+    b = static_cast<int>((static_cast<unsigned long long>(rem) * h_magic) >> 32);
+    h = rem - b * H;
   };
+  const bool has_dbias = G.dbias[0] != nullptr;       // (all groups agree: checked by the host)
 
   if (warp == kSoftmaxWarps) {
     // ================= control warp: TMA producer + MMA issuer (one lane) =================
     if (lane == 0 && n_my > 0) {
-      prefetch_tmap(&maps.qkv_a);
-      prefetch_tmap(&maps.qkv_b);
-      prefetch_tmap(&maps.do_a);
-      prefetch_tmap(&maps.do_b);
+      for (int g = 0; g * items_per_group < n_items; ++g) {
+        prefetch_tmap(&G.maps[g].qkv_a);
+        prefetch_tmap(&G.maps[g].qkv_b);
+        prefetch_tmap(&G.maps[g].do_a);
+        prefetch_tmap(&G.maps[g].do_b);
+      }
       const uint32_t idesc_dv = umma_idesc_bf16(128, HD, 0, 1);    // A K-major (TMEM / dS^T tile), B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // A = dS^T tile read MN-major, B MN-major
       auto load_item = [&](int item, bool prefetch_only) {
-        int b, h;
-        item_bh(item, b, h);
+        int cg, b, h;
+        item_bh(item, cg, b, h);
+        const BwdMaps& maps = G.maps[cg];
         if (!prefetch_only) mbar_arrive_expect_tx(tma_bar, 4 * op_bytes);
         for (int op = 0; op < 4; ++op) {      // Q, K, V (columns of qkv), dO
           const CUtensorMap* ma = op < 3 ? &maps.qkv_a : &maps.do_a;
@@ -544,13 +571,13 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
     auto compute_vectors = [&](int k) {
       const int t = threadIdx.x;
       if (t < 256) {
-        int b, h;
-        item_bh(first + k * stride, b, h);
+        int cg, b, h;
+        item_bh(first + k * stride, cg, b, h);
         float l2 = INFINITY, dd = 0.f;        // padding queries: P = exp2(-inf) = 0
         if (t < N) {
-          l2 = lse_g[(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
-          const uint4* po = reinterpret_cast<const uint4*>(o_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
-          const uint4* pg = reinterpret_cast<const uint4*>(do_g + (static_cast<size_t>(b) * N + t) * d + h * HD);
+          l2 = G.lse[cg][(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
+          const uint4* po = reinterpret_cast<const uint4*>(G.o[cg] + (static_cast<size_t>(b) * N + t) * d + h * HD);
+          const uint4* pg = reinterpret_cast<const uint4*>(G.d_o[cg] + (static_cast<size_t>(b) * N + t) * d + h * HD);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint4 a = po[i], g = pg[i];
@@ -568,7 +595,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
     };
     // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv.
     // The rounded values that were stored are returned in v (0 for rows past the sequence) for the bias gradient.
-    auto store_acc = [&](uint32_t tcol, float mul, int tok, int b, int col, float (&v)[16], bool accumulate_v) {
+    auto store_acc = [&](__nv_bfloat16* dqkv, uint32_t tcol, float mul, int tok, int b, int col, float (&v)[16], bool accumulate_v) {
       float f[16];
       tmem_ld_32x16(tcol + lane_off + grp * 16, f);
       tmem_ld_wait();
@@ -606,7 +633,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
     // V bias gradient without a reduction: sum_k dV[k,:] = sum_q (sum_k P[q,k]) dO[q,:] = sum_q dO[q,:].  When the
     // last key tile has a spare row (N % 128 != 0) its row 127 of P^T is set to 1 for every real query, so that
     // row of the dV accumulator IS the column sum (fp32, exact) and its 4 threads add it to dbias.
-    const bool ones_row = dbias != nullptr && (N & 127) != 0;
+    const bool ones_row = has_dbias && (N & 127) != 0;
     if (n_my > 0) compute_vectors(0);
     softmax_warps_sync();
     int cc = 0, pair = 0;
@@ -616,8 +643,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
       if (pend_kv >= 0) {
         mbar_wait(&pair_done[pend_kv_pair & 1], (pend_kv_pair >> 1) & 1);
         tc_fence_after();
-        int b, h;
-        item_bh(pend_kv_item, b, h);
+        int cg, b, h;
+        item_bh(pend_kv_item, cg, b, h);
+        float* dbias = G.dbias[cg];
+        __nv_bfloat16* dqkv = G.dqkv[cg];
         const int key = pend_kv * 128 + row;
         float v[16];
         if (ones_row && pend_kv == nkt - 1 && quarter == 3) {    // warp-uniform: tcgen05.ld is a whole-warp instruction
@@ -629,10 +658,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
             for (int c = 0; c < 16; ++c) atomicAdd(dbias + 2 * d + h * HD + grp * 16 + c, f[c]);
           }
         }
-        store_acc(tDV, 1.0f, key, b, 2 * d + h * HD, v, false);
+        store_acc(dqkv, tDV, 1.0f, key, b, 2 * d + h * HD, v, false);
         if (dbias != nullptr && !ones_row) add_colsum(v, dbias, 2 * d + h * HD);
         // the K bias gradient is identically zero (softmax is invariant to a shift of the scores): nothing to add
-        store_acc(tDK, scale, key, b, d + h * HD, v, false);
+        store_acc(dqkv, tDK, scale, key, b, d + h * HD, v, false);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
@@ -641,10 +670,11 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const __nv_bfloat16* __
       if (pend_dq_item >= 0) {
         mbar_wait(&pair_done[pend_dq_pair & 1], (pend_dq_pair >> 1) & 1);
         tc_fence_after();
-        int b, h;
-        item_bh(pend_dq_item, b, h);
+        int cg, b, h;
+        item_bh(pend_dq_item, cg, b, h);
+        float* dbias = G.dbias[cg];
         float v[16];                          // both query tiles summed per thread: one reduction per item
-        for (int qt = 0; qt < nkt; ++qt) store_acc(tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, v, qt > 0);
+        for (int qt = 0; qt < nkt; ++qt) store_acc(G.dqkv[cg], tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, v, qt > 0);
         if (dbias != nullptr) add_colsum(v, dbias, h * HD);
         tc_fence_before();
         __syncwarp();
@@ -763,21 +793,28 @@ int make_tmap3(CUtensorMap* m, const void* ptr, int B, int N, int width, int row
 
 }  // namespace
 
-extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim,
-                                int device, void* stream) {
+extern "C" int fc_attention_fwd_grouped(int groups, const void* const* qkv, void* const* out, float* const* lse, int B,
+                                        int N, int H, int head_dim, int device, void* stream) {
+  FC_REQUIRE(groups >= 1 && groups <= MAXG, "fc_attention_fwd: %d groups (1..%d)", groups, MAXG);
   FC_REQUIRE(head_dim == HD, "fc_attention_fwd: head_dim must be 64 (got %d)", head_dim);
   FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
              "fc_attention_fwd: unsupported shape B=%d N=%d H=%d", B, N, H);
-  FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-             "fc_attention_fwd: qkv/out must be 16-byte aligned");
   FcDeviceGuard guard(device);
   const int RA = N > 128 ? 128 : ((N + 15) & ~15);
   const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
   const int NK = RA + RB;
-  FwdMaps maps;
-  int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
-  if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
-  if (rc) return rc;
+  FwdGroups G;
+  memset(&G, 0, sizeof(G));
+  for (int g = 0; g < groups; ++g) {
+    FC_REQUIRE(qkv[g] != nullptr && out[g] != nullptr, "fc_attention_fwd: null tensor (group %d)", g);
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv[g]) & 15) == 0 && (reinterpret_cast<uintptr_t>(out[g]) & 15) == 0,
+               "fc_attention_fwd: qkv/out must be 16-byte aligned");
+    int rc = make_tmap3(&G.maps[g].qkv_a, qkv[g], B, N, 3 * H * HD, RA);
+    if (!rc) rc = make_tmap3(&G.maps[g].qkv_b, qkv[g], B, N, 3 * H * HD, RB ? RB : RA);
+    if (rc) return rc;
+    G.out[g] = static_cast<__nv_bfloat16*>(out[g]);
+    G.lse[g] = lse ? lse[g] : nullptr;
+  }
   const int buf_bytes = 3 * NK * 128, aux = 6144 + 128;
   int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
   while (nbuf > 1 && nbuf * buf_bytes + aux > kMaxDynSmem) --nbuf;
@@ -787,44 +824,67 @@ extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, i
   const int pad = buf_bytes < TILE ? TILE - buf_bytes : 0;
   const int smem = nbuf * buf_bytes + aux + pad;
   FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
-  const int items = B * H;
+  const int items = groups * B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
   const int grid = fc_apply_grid_cap((items + waves - 1) / waves);   // balanced persistent grid (<= #SMs)
   const float scale_log2e = 0.125f * 1.4426950408889634f;        // 64^-0.5 * log2(e)
-  attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      maps, static_cast<__nv_bfloat16*>(out), lse, items, N, H, nbuf, scale_log2e);
+  attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, nbuf,
+                                                                                          scale_log2e);
+  FC_LAUNCH_CHECK();
+  return FC_OK;
+}
+
+extern "C" int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int head_dim,
+                                int device, void* stream) {
+  return fc_attention_fwd_grouped(1, &qkv, &out, &lse, B, N, H, head_dim, device, stream);
+}
+
+extern "C" int fc_attention_bwd_grouped(int groups, const void* const* qkv, const void* const* out,
+                                        const void* const* d_out, const float* const* lse, void* const* dqkv,
+                                        float* const* dbias, int B, int N, int H, int head_dim, int device, void* stream) {
+  FC_REQUIRE(groups >= 1 && groups <= MAXG, "fc_attention_bwd: %d groups (1..%d)", groups, MAXG);
+  FC_REQUIRE(head_dim == HD, "fc_attention_bwd: head_dim must be 64 (got %d)", head_dim);
+  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
+             "fc_attention_bwd: unsupported shape B=%d N=%d H=%d", B, N, H);
+  FcDeviceGuard guard(device);
+  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
+  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
+  const int NK = RA + RB;
+  BwdGroups G;
+  memset(&G, 0, sizeof(G));
+  for (int g = 0; g < groups; ++g) {
+    FC_REQUIRE(qkv[g] && out[g] && d_out[g] && lse[g] && dqkv[g], "fc_attention_bwd: null tensor (group %d)", g);
+    FC_REQUIRE(((reinterpret_cast<uintptr_t>(qkv[g]) | reinterpret_cast<uintptr_t>(out[g]) |
+                 reinterpret_cast<uintptr_t>(d_out[g]) | reinterpret_cast<uintptr_t>(dqkv[g])) & 15) == 0,
+               "fc_attention_bwd: tensors must be 16-byte aligned");
+    FC_REQUIRE(((dbias ? dbias[g] : nullptr) == nullptr) == ((dbias ? dbias[0] : nullptr) == nullptr),
+               "fc_attention_bwd: groups disagree on dbias");
+    BwdMaps& m = G.maps[g];
+    int rc = make_tmap3(&m.qkv_a, qkv[g], B, N, 3 * H * HD, RA);
+    if (!rc) rc = make_tmap3(&m.qkv_b, qkv[g], B, N, 3 * H * HD, RB ? RB : RA);
+    if (!rc) rc = make_tmap3(&m.do_a, d_out[g], B, N, H * HD, RA);
+    if (!rc) rc = make_tmap3(&m.do_b, d_out[g], B, N, H * HD, RB ? RB : RA);
+    if (rc) return rc;
+    G.o[g] = static_cast<const __nv_bfloat16*>(out[g]);
+    G.d_o[g] = static_cast<const __nv_bfloat16*>(d_out[g]);
+    G.lse[g] = lse[g];
+    G.dqkv[g] = static_cast<__nv_bfloat16*>(dqkv[g]);
+    G.dbias[g] = dbias ? dbias[g] : nullptr;
+  }
+  const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
+  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
+  const int items = groups * B * H;
+  const int sms = fc_num_sms(device);
+  const int waves = (items + sms - 1) / sms;
+  const int grid = fc_apply_grid_cap((items + waves - 1) / waves);
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, 0.125f);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
 
 extern "C" int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                                 float* dbias, int B, int N, int H, int head_dim, int device, void* stream) {
-  FC_REQUIRE(head_dim == HD, "fc_attention_bwd: head_dim must be 64 (got %d)", head_dim);
-  FC_REQUIRE(B > 0 && N > 0 && N <= 256 && H > 0 && static_cast<long long>(B) * H < 65536,
-             "fc_attention_bwd: unsupported shape B=%d N=%d H=%d", B, N, H);
-  FC_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) |
-               reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
-             "fc_attention_bwd: tensors must be 16-byte aligned");
-  FcDeviceGuard guard(device);
-  const int RA = N > 128 ? 128 : ((N + 15) & ~15);
-  const int RB = N > 128 ? ((N - 128 + 15) & ~15) : 0;
-  const int NK = RA + RB;
-  BwdMaps maps;
-  int rc = make_tmap3(&maps.qkv_a, qkv, B, N, 3 * H * HD, RA);
-  if (!rc) rc = make_tmap3(&maps.qkv_b, qkv, B, N, 3 * H * HD, RB ? RB : RA);
-  if (!rc) rc = make_tmap3(&maps.do_a, d_out, B, N, H * HD, RA);
-  if (!rc) rc = make_tmap3(&maps.do_b, d_out, B, N, H * HD, RB ? RB : RA);
-  if (rc) return rc;
-  const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
-  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
-  const int items = B * H;
-  const int sms = fc_num_sms(device);
-  const int waves = (items + sms - 1) / sms;
-  const int grid = fc_apply_grid_cap((items + waves - 1) / waves);
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      maps, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(d_out), lse,
-      static_cast<__nv_bfloat16*>(dqkv), dbias, items, N, H, 0.125f);
-  FC_LAUNCH_CHECK();
-  return FC_OK;
+  void* dq = dqkv;
+  return fc_attention_bwd_grouped(1, &qkv, &out, &d_out, &lse, &dq, &dbias, B, N, H, head_dim, device, stream);
 }

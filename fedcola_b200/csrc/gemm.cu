@@ -61,43 +61,58 @@ template <int BN, int EPI, int PAIR> struct Cfg {
   static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 16 <= 1024, "barrier block");
 };
 
-struct GemmParams {
-  int M, N, K;              // output rows, output cols, reduction length
-  int kb_per_split, splits; // K blocks handled by one split; number of splits
-  int m_tiles, n_tiles;
-  int epi;
-  int ldo;                  // leading dimension (elements) of out/out2/resid/aux
+// Client groups: one launch can run the SAME GEMM (shape, majors, epilogue) for up to FC_GEMM_MAX_GROUPS independent
+// operand sets — the same layer of several clients trained in lockstep.  Tiles of all groups share one persistent
+// walk, so the per-launch fixed costs (prologue, first-load latency, exposed last epilogue, wave quantisation) are
+// paid once per group of clients instead of once per client.
+struct GroupPtrs {
   void* out;
   void* out2;
   const float* bias;        // [N] or null
   const float* resid;       // EPI_RESID: fp32 [M, ldo]
-  const float* row_scale;   // per-group scale (DropPath keep/keep_prob), index = row / rows_per_group; or null
-  int rows_per_group;
+  const float* row_scale;   // per-sample scale (DropPath keep/keep_prob), index = row / rows_per_group; or null
   const __nv_bfloat16* aux; // EPI_MULAUX: bf16 multiplier [M, ldo] (gelu'(pre) saved by the forward)
   float* colsum;            // EPI_MULAUX: += column sums of the output (bias gradient), or null
   const float* pos;         // EPI_PATCH: pos_embed [(P+1), N]
+};
+struct GroupMaps { CUtensorMap a, b, o, o2, r; };
+struct AllMaps { GroupMaps g[FC_GEMM_MAX_GROUPS]; };
+
+struct GemmParams {
+  int M, N, K;              // output rows, output cols, reduction length (of every group)
+  int kb_per_split, splits; // K blocks handled by one split; number of splits
+  int m_tiles, n_tiles;
+  int groups;
+  int epi;
+  int ldo;                  // leading dimension (elements) of out/out2/resid/aux
+  int rows_per_group;
   int patches;              // EPI_PATCH: P (196)
   float alpha;
   int debug;                // measurement aid (FC_GEMM_DEBUG env): 1 = skip epilogue work, 2 = skip TMA+MMA work
   int pair;                 // 1: CTA pairs (cta_group::2) compute 256 x BN tiles, each CTA stages its 128 rows of A and half of B
+  GroupPtrs g[FC_GEMM_MAX_GROUPS];
 };
 
 // Persistent tile walk.  pair == 0: tile t = blockIdx.x, +gridDim.x, ... -> (split, m_blk, n_blk), n fastest.
 // pair == 1: the CTA pair (blockIdx.x >> 1) walks pair-tiles (split, m_pair, n_blk); rank r owns m_blk = 2*m_pair + r
 // (an M tile past the matrix is all TMA zero fill / clipped stores).
 template <int PAIR> struct TileWalk {
-  int first, step, total, tiles_mn, n_tiles, rank;
+  int first, step, total, tiles_mn, per_group, n_tiles, rank;
   __device__ TileWalk(const GemmParams& p) {
     rank = PAIR ? static_cast<int>(blockIdx.x & 1) : 0;
     first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     n_tiles = p.n_tiles;
     tiles_mn = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
-    total = tiles_mn * p.splits;
+    per_group = tiles_mn * p.splits;
+    total = per_group * p.groups;
   }
-  __device__ void decode(int tile, int& split, int& m_blk, int& n_blk) const {
-    split = tile / tiles_mn;
-    const int mn = tile - split * tiles_mn;
+  // tile -> (group, split, m_blk, n_blk): n fastest (CTAs running side by side share the A rows in L2), group slowest
+  __device__ void decode(int tile, int& grp, int& split, int& m_blk, int& n_blk) const {
+    grp = tile / per_group;
+    const int t = tile - grp * per_group;
+    split = t / tiles_mn;
+    const int mn = t - split * tiles_mn;
     const int mq = mn / n_tiles;
     n_blk = mn - mq * n_tiles;
     m_blk = PAIR ? 2 * mq + rank : mq;
@@ -145,7 +160,7 @@ template <> struct EpiPre<FC_EPI_RESID> { float4 x[8]; float sc[8]; };
 template <> struct EpiPre<FC_EPI_MULAUX> { uint2 q[8]; };   // (legacy register-prefetch path; PATCH is its only user now)
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EPI>& pre, int row_base, int col0, int lane) {
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, const GroupPtrs& gp, EpiPre<EPI>& pre, int row_base, int col0, int lane) {
   const int col = col0 + (lane & 7) * 4;
   const int r0 = row_base + (lane >> 3);
   if constexpr (EPI == FC_EPI_RESID) {
@@ -155,8 +170,8 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EP
       pre.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       pre.sc[i] = 1.0f;
       if (col < p.N && row < p.M) {
-        pre.x[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + col);
-        if (p.row_scale) pre.sc[i] = __ldg(p.row_scale + row / p.rows_per_group);
+        pre.x[i] = *reinterpret_cast<const float4*>(gp.resid + static_cast<size_t>(row) * p.ldo + col);
+        if (gp.row_scale) pre.sc[i] = __ldg(gp.row_scale + row / p.rows_per_group);
       }
     }
   } else if constexpr (EPI == FC_EPI_MULAUX) {
@@ -164,7 +179,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EP
     for (int i = 0; i < 8; ++i) {
       const int row = r0 + 4 * i;
       pre.q[i] = make_uint2(0u, 0u);
-      if (col < p.N && row < p.M) pre.q[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<size_t>(row) * p.ldo + col);
+      if (col < p.N && row < p.M) pre.q[i] = *reinterpret_cast<const uint2*>(gp.aux + static_cast<size_t>(row) * p.ldo + col);
     }
   }
 }
@@ -174,7 +189,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPre<EP
 // global access of the warp covers 4 rows x (128 B fp32 | 64 B bf16) contiguous segments.
 // EPI is a compile-time constant: one lean instruction stream per fused op.  H = which 16-row pass.
 template <int EPI, int H>
-__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t stage, int row_base, int col0, int lane,
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const GroupPtrs& gp, uint32_t stage, int row_base, int col0, int lane,
                                                float4 bias, const EpiPre<EPI>& pre) {
   const int rsub = lane >> 3, col = col0 + (lane & 7) * 4;
   const bool col_ok = col < p.N;                 // N is a multiple of 8, col a multiple of 4
@@ -193,14 +208,14 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
   const size_t rstep = static_cast<size_t>(4) * p.ldo;
 
   if constexpr (EPI == FC_EPI_BF16) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(gp.out) + o0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) *reinterpret_cast<uint2*>(out + i * rstep) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
   } else if constexpr (EPI == FC_EPI_GELU) {
     // out = gelu'(pre) (what the backward needs), out2 = gelu(pre) (the fc2 operand); Phi and exp are shared
-    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
-    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + o0;
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(gp.out) + o0;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(gp.out2) + o0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) {
@@ -217,7 +232,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
         *reinterpret_cast<uint2*>(o2 + i * rstep) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
       }
   } else if constexpr (EPI == FC_EPI_RESID) {
-    float* out = reinterpret_cast<float*>(p.out) + o0;
+    float* out = reinterpret_cast<float*>(gp.out) + o0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) {
@@ -227,7 +242,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
             make_float4(x.x + sc * v[i].x, x.y + sc * v[i].y, x.z + sc * v[i].z, x.w + sc * v[i].w);
       }
   } else if constexpr (EPI == FC_EPI_MULAUX) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(gp.out) + o0;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -242,21 +257,21 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
         cs.x += a.x; cs.y += a.y; cs.z += b.x; cs.w += b.y;
       }
-    if (p.colsum != nullptr) {            // 16 rows of this block: lanes l, l+8, l+16, l+24 share the columns
+    if (gp.colsum != nullptr) {            // 16 rows of this block: lanes l, l+8, l+16, l+24 share the columns
 #pragma unroll
       for (int o = 8; o <= 16; o <<= 1) {
         cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
         cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
       }
-      if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs.x, cs.y, cs.z, cs.w);
+      if (lane < 8 && col_ok) red_add_v4(gp.colsum + col, cs.x, cs.y, cs.z, cs.w);
     }
   } else if constexpr (EPI == FC_EPI_F32) {
-    float* out = reinterpret_cast<float*>(p.out) + o0;
+    float* out = reinterpret_cast<float*>(gp.out) + o0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) *reinterpret_cast<float4*>(out + i * rstep) = v[i];
   } else if constexpr (EPI == FC_EPI_ATOMIC_F32) {
-    float* out = reinterpret_cast<float*>(p.out) + o0;
+    float* out = reinterpret_cast<float*>(gp.out) + o0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) red_add_v4(out + i * rstep, p.alpha * v[i].x, p.alpha * v[i].y, p.alpha * v[i].z, p.alpha * v[i].w);
@@ -271,10 +286,10 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t sta
       if (ok[i]) {
         const int row = r0 + 4 * i, b = row / p.patches, t = row - b * p.patches;
         orow[i] = b * (p.patches + 1) + 1 + t;
-        e[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + t) * p.N + col));
+        e[i] = __ldg(reinterpret_cast<const float4*>(gp.pos + static_cast<size_t>(1 + t) * p.N + col));
       }
     }
-    float* out = reinterpret_cast<float*>(p.out);
+    float* out = reinterpret_cast<float*>(gp.out);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i])
@@ -334,7 +349,7 @@ __device__ __forceinline__ void stage_acquire(int lane) {
 
 // One 32-row x kCW-column chunk of the accumulator (acc[] = this lane's row) -> global, fused op EPI.
 template <int EPI>
-__device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmO2,
+__device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const GroupPtrs& gp, const CUtensorMap* tmO, const CUtensorMap* tmO2,
                                                    uint8_t* buf_ptr, uint32_t buf, uint32_t bias_smem, uint64_t* ebar,
                                                    uint32_t& eph, float (&acc)[EpiTraits<EPI>::kCW], int row0, int col0,
                                                    int lane) {
@@ -342,7 +357,7 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
   const int t = lane;
   // bias of the chunk's columns was staged in shared memory by this warp (one coalesced load, issued before the
   // TMEM read): every lane needs all of it -> broadcast LDS.128
-  if (p.bias != nullptr) {
+  if (gp.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) {
       const float4 b = lds_v4(bias_smem + 16 * j);
@@ -381,7 +396,7 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
     stage_store<false>(tmO2, buf_ptr, col0, row0, lane);
   } else if constexpr (EPI == FC_EPI_RESID) {
     const int row = row0 + t;
-    const float sc = (p.row_scale != nullptr && row < p.M) ? __ldg(p.row_scale + row / p.rows_per_group) : 1.0f;
+    const float sc = (gp.row_scale != nullptr && row < p.M) ? __ldg(gp.row_scale + row / p.rows_per_group) : 1.0f;
     mbar_wait(ebar, eph);                       // residual tile has landed in the staging buffer
     eph ^= 1;
 #pragma unroll
@@ -402,7 +417,7 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
       sts_u4(a, pack_bf16(acc[8 * j] * q0.x, acc[8 * j + 1] * q0.y), pack_bf16(acc[8 * j + 2] * q1.x, acc[8 * j + 3] * q1.y),
              pack_bf16(acc[8 * j + 4] * q2.x, acc[8 * j + 5] * q2.y), pack_bf16(acc[8 * j + 6] * q3.x, acc[8 * j + 7] * q3.y));
     }
-    if (p.colsum != nullptr) {                  // bias gradient: column sums of the bf16 values just staged
+    if (gp.colsum != nullptr) {                  // bias gradient: column sums of the bf16 values just staged
       __syncwarp();
       float s0 = 0.f, s1 = 0.f;                 // lane owns columns 2*lane, 2*lane+1 of the tile
 #pragma unroll 8
@@ -413,8 +428,8 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
       }
       const int c = col0 + 2 * lane;
       if (c < p.N) {
-        atomicAdd(p.colsum + c, s0);
-        atomicAdd(p.colsum + c + 1, s1);
+        atomicAdd(gp.colsum + c, s0);
+        atomicAdd(gp.colsum + c + 1, s1);
       }
     }
     stage_store<false>(tmO, buf_ptr, col0, row0, lane);
@@ -438,9 +453,7 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const CU
 // epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int A_MN, int B_MN, int EPI, int PAIR>
 __global__ void __launch_bounds__(gemm_threads_for(EPI), 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
-                 const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, EPI, PAIR>;
   constexpr int STAGES = C::STAGES;
   constexpr bool pair = PAIR != 0;
@@ -462,12 +475,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const TileWalk<PAIR> walk(p);
   // pair mode: both CTAs use the same stage offsets; the leader's MMAs read A and B from both shared memories.
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    if (EPI != FC_EPI_PATCH) prefetch_tmap(&tmO);
-    if (EPI == FC_EPI_GELU) prefetch_tmap(&tmO2);
-    if (EpiTraits<EPI>::kLoads) prefetch_tmap(&tmR);
+  if (warp == 0 && lane < p.groups) {
+    const GroupMaps& gm = maps.g[lane];
+    prefetch_tmap(&gm.a);
+    prefetch_tmap(&gm.b);
+    if (EPI != FC_EPI_PATCH) prefetch_tmap(&gm.o);
+    if (EPI == FC_EPI_GELU) prefetch_tmap(&gm.o2);
+    if (EpiTraits<EPI>::kLoads) prefetch_tmap(&gm.r);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -501,8 +515,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int tile = walk.first; tile < walk.total; tile += walk.step) {
-        int split, m_blk, n_blk;
-        walk.decode(tile, split, m_blk, n_blk);
+        int grp, split, m_blk, n_blk;
+        walk.decode(tile, grp, split, m_blk, n_blk);
+        const CUtensorMap* tmA = &maps.g[grp].a;
+        const CUtensorMap* tmB = &maps.g[grp].b;
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = (p.debug & 2) ? kb1 : kb0; kb < kb1; ++kb) {
@@ -517,31 +533,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
             if (walk.rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
             if (A_MN) {
-              tma_load_2d_pair(a_dst, &tmA, lbar, m0, kb * BK);
-              tma_load_2d_pair(a_dst + 8192, &tmA, lbar, m0 + 64, kb * BK);
+              tma_load_2d_pair(a_dst, tmA, lbar, m0, kb * BK);
+              tma_load_2d_pair(a_dst + 8192, tmA, lbar, m0 + 64, kb * BK);
             } else {
-              tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
+              tma_load_2d_pair(a_dst, tmA, lbar, kb * BK, m0);
             }
             const int nh = n0 + walk.rank * (BN / 2);          // this CTA's half of the B tile
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(b_dst + j * 8192, &tmB, lbar, nh + j * 64, kb * BK);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(b_dst + j * 8192, tmB, lbar, nh + j * 64, kb * BK);
             } else {      // box {64 (k), BN/2 (n)}
-              tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, nh);
+              tma_load_2d_pair(b_dst, tmB, lbar, kb * BK, nh);
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
             if (A_MN) {   // [K, M] global: boxes {64 (m), 64 (k)}
-              tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
-              tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
+              tma_load_2d(a_dst, tmA, &full_bar[s], m0, kb * BK);
+              tma_load_2d(a_dst + 8192, tmA, &full_bar[s], m0 + 64, kb * BK);
             } else {      // [M, K] global: box {64 (k), 128 (m)}
-              tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+              tma_load_2d(a_dst, tmA, &full_bar[s], kb * BK, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, tmB, &full_bar[s], n0 + j * 64, kb * BK);
             } else {      // box {64 (k), BN (n)}
-              tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+              tma_load_2d(b_dst, tmB, &full_bar[s], kb * BK, n0);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -555,7 +571,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       int it = 0;
       for (int tile = walk.first; tile < walk.total; tile += walk.step, ++it) {
-        const int split = tile / walk.tiles_mn;
+        const int split = (tile % walk.per_group) / walk.tiles_mn;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const int buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
@@ -611,8 +627,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else mbar_arrive(&tmem_empty_bar[b]);
     };
     for (int tile = walk.first; tile < walk.total; tile += walk.step, ++it) {
-      int split_unused, m_blk, n_blk;
-      walk.decode(tile, split_unused, m_blk, n_blk);
+      int grp, split_unused, m_blk, n_blk;
+      walk.decode(tile, grp, split_unused, m_blk, n_blk);
+      const GroupPtrs& gp = p.g[grp];
+      const CUtensorMap* tmO = &maps.g[grp].o;
+      const CUtensorMap* tmO2 = &maps.g[grp].o2;
+      const CUtensorMap* tmR = &maps.g[grp].r;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int buf_i = it & 1;
       mbar_wait(&tmem_full_bar[buf_i], (it >> 1) & 1);
@@ -636,7 +656,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // legacy path (row remap b*P+t -> b*(P+1)+1+t cannot be expressed as one TMA box): transpose via smem
           float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
           const int bcol = col0 + (lane & 7) * 4;
-          if (p.bias != nullptr && bcol < p.N) bias = __ldg(reinterpret_cast<const float4*>(p.bias + bcol));
+          if (gp.bias != nullptr && bcol < p.N) bias = __ldg(reinterpret_cast<const float4*>(gp.bias + bcol));
           EpiPre<EPI> pre;
           float acc[32];
           tmem_ld_32x32(taddr + c * 32, acc);
@@ -652,7 +672,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sts_v4(buf + (lane * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           }
           __syncwarp();
-          epilogue_block<EPI, 0>(p, buf, row0, col0, lane, bias, pre);
+          epilogue_block<EPI, 0>(p, gp, buf, row0, col0, lane, bias, pre);
           __syncwarp();
           if (lane >= 16) {
 #pragma unroll
@@ -660,20 +680,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sts_v4(buf + ((lane - 16) * STAGE_LD + j * 4) * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           }
           __syncwarp();
-          epilogue_block<EPI, 1>(p, buf, row0, col0, lane, bias, pre);
+          epilogue_block<EPI, 1>(p, gp, buf, row0, col0, lane, bias, pre);
           __syncwarp();
         } else {
           if constexpr (EpiTraits<EPI>::kLoads) {     // fused operand tile (residual / saved gelu') -> staging buffer
             if (lane == 0) {
               tma_store_wait_read();           // the previous store out of this buffer has drained
               mbar_arrive_expect_tx(ebar, EPI_BUF_BYTES);
-              tma_load_2d(buf_ptr, &tmR, ebar, col0, row0);
+              tma_load_2d(buf_ptr, tmR, ebar, col0, row0);
             }
           }
           // the chunk's bias: lane l fetches columns col0 + 2l, 2l+1 now (latency overlaps the TMEM read) ...
           float2 b2 = make_float2(0.f, 0.f);
-          if (p.bias != nullptr && 2 * lane < CW && col0 + 2 * lane < p.N)
-            b2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + 2 * lane));
+          if (gp.bias != nullptr && 2 * lane < CW && col0 + 2 * lane < p.N)
+            b2 = __ldg(reinterpret_cast<const float2*>(gp.bias + col0 + 2 * lane));
           float acc[CW];
           {
             float(&lo)[32] = *reinterpret_cast<float(*)[32]>(&acc[0]);
@@ -689,12 +709,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) release_acc(buf_i);
           }
-          if (p.bias != nullptr) {             // ... and shares it with the other lanes through shared memory
+          if (gp.bias != nullptr) {             // ... and shares it with the other lanes through shared memory
             if (2 * lane < CW)
               asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_smem + 8 * lane), "f"(b2.x), "f"(b2.y) : "memory");
             __syncwarp();
           }
-          epilogue_tma_chunk<EPI>(p, &tmO, &tmO2, buf_ptr, buf, bias_smem, ebar, eph, acc, row0, col0, lane);
+          epilogue_tma_chunk<EPI>(p, gp, tmO, tmO2, buf_ptr, buf, bias_smem, ebar, eph, acc, row0, col0, lane);
         }
       }
     }
@@ -749,27 +769,24 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 int g_prof_on = 0;
 
-struct EpiMaps { CUtensorMap o, o2, r; };
-
 template <int BN, int A_MN, int B_MN, int EPI, int PAIR>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int device,
-           cudaStream_t st) {
+int launch(const AllMaps& maps, const GemmParams& p, int device, cudaStream_t st) {
   using C = Cfg<BN, EPI, PAIR>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, PAIR>;
   FC_SMEM_OPT_IN(kern, (C::SMEM_BYTES));
   int grid = fc_num_sms(device);
   if (PAIR) {
-    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits * p.groups;
     grid &= ~1;
     if (grid > 2 * pair_tiles) grid = 2 * pair_tiles;
     grid = fc_apply_grid_cap(grid) & ~1;
     if (grid < 2) grid = 2;
   } else {
-    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits * p.groups;
     if (grid > total_tiles) grid = total_tiles;
     grid = fc_apply_grid_cap(grid);
   }
-  ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K};
+  ProfRec rec{nullptr, nullptr, 2.0 * p.M * (double)p.N * p.K * p.groups};
   const bool prof = __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) != 0;
   if (prof) {
     cudaEventCreate(&rec.a);
@@ -789,9 +806,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.o, em.o2, em.r, p));
+    FC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps, p));
   } else {
-    kern<<<grid, gemm_threads_for(EPI), C::SMEM_BYTES, st>>>(ta, tb, em.o, em.o2, em.r, p);
+    kern<<<grid, gemm_threads_for(EPI), C::SMEM_BYTES, st>>>(maps, p);
   }
   if (prof) {
     cudaEventRecord(rec.b, st);
@@ -810,10 +827,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, cons
 // each as a single-CTA kernel (128 x BN tiles) and — except PATCH, and BN = 192 with an MN-major B whose half tile is
 // not a whole number of 64-column blocks — as a CTA-pair kernel (cta_group::2, 256 x BN tiles).
 template <int BN, int PAIR>
-int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int a_mn, int b_mn,
-              int device, cudaStream_t st) {
+int launch_bn(const AllMaps& maps, const GemmParams& p, int a_mn, int b_mn, int device, cudaStream_t st) {
 #define FC_CASE(AM, BMJ, E) \
-  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E, PAIR>(ta, tb, em, p, device, st)
+  if (a_mn == AM && b_mn == BMJ && p.epi == E) return launch<BN, AM, BMJ, E, PAIR>(maps, p, device, st)
   FC_CASE(0, 0, FC_EPI_BF16); FC_CASE(0, 0, FC_EPI_GELU); FC_CASE(0, 0, FC_EPI_RESID); FC_CASE(0, 0, FC_EPI_F32);
   if constexpr (!PAIR) { FC_CASE(0, 0, FC_EPI_PATCH); }
   if constexpr (!PAIR || BN % 128 == 0) {
@@ -828,7 +844,7 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, c
 
 // Tile width: minimise (waves over the SMs) x (per-tile cost ~ BN + fixed overhead), i.e. trade the better
 // operand reuse of wide tiles against wave quantisation and zero-padded columns.
-int pick_bn(int M, int N, int splits, int sms) {
+int pick_bn(int M, int N, int splits, int sms) {      // splits: K splits x client groups
   const int cands[3] = {256, 192, 128};
   int best = 128;
   double best_cost = 1e30;
@@ -866,21 +882,30 @@ extern "C" long long fc_gemm_profile_collect(double* total_ms, double* total_flo
   return (long long)g_prof.size();
 }
 
-extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
-                            long long ldb, int b_mn_major, int epi, void* out, void* out2, long long ldo,
-                            const float* bias, const float* resid, const float* row_scale, int rows_per_group,
-                            const void* aux, const float* pos, int patches, float alpha, int splits,
-                            float* colsum, int device, void* stream) {
+extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void* const* A, long long lda, int a_mn_major,
+                                    const void* const* B, long long ldb, int b_mn_major, int epi, void* const* out,
+                                    void* const* out2, long long ldo, const float* const* bias,
+                                    const float* const* resid, const float* const* row_scale, int rows_per_group,
+                                    const void* const* aux, const float* const* pos, int patches, float alpha,
+                                    int splits, float* const* colsum, int device, void* stream) {
+  FC_REQUIRE(groups >= 1 && groups <= FC_GEMM_MAX_GROUPS, "fc_gemm_bf16: %d groups (1..%d)", groups, FC_GEMM_MAX_GROUPS);
   FC_REQUIRE(M > 0 && N > 0 && K > 0, "fc_gemm_bf16: empty problem %d %d %d", M, N, K);
   FC_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 4 == 0, "fc_gemm_bf16: N, lda, ldb must be multiples of 8");
   FC_REQUIRE(epi >= FC_EPI_BF16 && epi <= FC_EPI_PATCH, "fc_gemm_bf16: bad epilogue %d", epi);
-  FC_REQUIRE(out != nullptr, "fc_gemm_bf16: null output");
-  FC_REQUIRE(epi != FC_EPI_GELU || out2 != nullptr, "fc_gemm_bf16: GELU epilogue needs out2");
-  FC_REQUIRE(epi != FC_EPI_RESID || resid != nullptr, "fc_gemm_bf16: RESID epilogue needs resid");
-  FC_REQUIRE(epi != FC_EPI_MULAUX || aux != nullptr, "fc_gemm_bf16: MULAUX epilogue needs aux");
-  FC_REQUIRE(colsum == nullptr || epi == FC_EPI_MULAUX, "fc_gemm_bf16: colsum is only fused into the MULAUX epilogue");
-  FC_REQUIRE(epi != FC_EPI_PATCH || (pos != nullptr && patches > 0), "fc_gemm_bf16: PATCH epilogue needs pos");
-  FC_REQUIRE(row_scale == nullptr || rows_per_group > 0, "fc_gemm_bf16: rows_per_group");
+  FC_REQUIRE(A != nullptr && B != nullptr && out != nullptr, "fc_gemm_bf16: null operand table");
+  auto at = [](auto tbl, int g) { return tbl ? tbl[g] : nullptr; };
+  for (int g = 0; g < groups; ++g) {
+    FC_REQUIRE(A[g] != nullptr && B[g] != nullptr && out[g] != nullptr, "fc_gemm_bf16: null operand / output (group %d)", g);
+    FC_REQUIRE(epi != FC_EPI_GELU || at(out2, g) != nullptr, "fc_gemm_bf16: GELU epilogue needs out2");
+    FC_REQUIRE(epi != FC_EPI_RESID || at(resid, g) != nullptr, "fc_gemm_bf16: RESID epilogue needs resid");
+    FC_REQUIRE(epi != FC_EPI_MULAUX || at(aux, g) != nullptr, "fc_gemm_bf16: MULAUX epilogue needs aux");
+    FC_REQUIRE(at(colsum, g) == nullptr || epi == FC_EPI_MULAUX, "fc_gemm_bf16: colsum is only fused into the MULAUX epilogue");
+    FC_REQUIRE(epi != FC_EPI_PATCH || (at(pos, g) != nullptr && patches > 0), "fc_gemm_bf16: PATCH epilogue needs pos");
+    // the epilogue branches on these once per launch: all groups must agree on which optional operands exist
+    FC_REQUIRE((at(bias, g) == nullptr) == (at(bias, 0) == nullptr) && (at(row_scale, g) == nullptr) == (at(row_scale, 0) == nullptr) &&
+               (at(colsum, g) == nullptr) == (at(colsum, 0) == nullptr), "fc_gemm_bf16: groups disagree on optional operands");
+  }
+  FC_REQUIRE(at(row_scale, 0) == nullptr || rows_per_group > 0, "fc_gemm_bf16: rows_per_group");
   FcDeviceGuard guard(device);
   const int total_kb = (K + BK - 1) / BK;
   const int sms = fc_num_sms(device);
@@ -891,7 +916,7 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
     const int cands[3] = {256, 192, 128};
     const int max_s = total_kb / 2 > 1 ? (total_kb / 2 < 64 ? total_kb / 2 : 64) : 1;
     for (int c : cands) {
-      const long long base = (long long)((M + BM - 1) / BM) * ((N + c - 1) / c);
+      const long long base = (long long)((M + BM - 1) / BM) * ((N + c - 1) / c) * groups;
       for (int sp = 1; sp <= max_s; ++sp) {
         const int per = (total_kb + sp - 1) / sp;
         const long long tiles = base * ((total_kb + per - 1) / per);
@@ -905,17 +930,22 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
   if (splits > total_kb) splits = total_kb;
   FC_REQUIRE(splits == 1 || epi == FC_EPI_ATOMIC_F32, "fc_gemm_bf16: split-K needs the atomic epilogue");
   GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
+  p.groups = groups;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  if (bn == 0) bn = pick_bn(M, N, p.splits, sms);
+  if (bn == 0) bn = pick_bn(M, N, p.splits * groups, sms);
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + bn - 1) / bn;
   p.epi = epi; p.ldo = static_cast<int>(ldo);
-  p.out = out; p.out2 = out2; p.bias = bias; p.resid = resid; p.row_scale = row_scale;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
-  p.aux = reinterpret_cast<const __nv_bfloat16*>(aux); p.pos = pos; p.patches = patches; p.alpha = alpha;
-  p.colsum = colsum;
+  p.patches = patches; p.alpha = alpha;
+  for (int g = 0; g < groups; ++g) {
+    GroupPtrs& q = p.g[g];
+    q.out = out[g]; q.out2 = at(out2, g); q.bias = at(bias, g); q.resid = at(resid, g); q.row_scale = at(row_scale, g);
+    q.aux = reinterpret_cast<const __nv_bfloat16*>(at(aux, g)); q.pos = at(pos, g); q.colsum = at(colsum, g);
+  }
   {
     static const int dbg = getenv("FC_GEMM_DEBUG") ? atoi(getenv("FC_GEMM_DEBUG")) : 0;
     p.debug = dbg;
@@ -930,43 +960,57 @@ extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, i
     }
     p.pair = (use_pairs && epi != FC_EPI_PATCH && (!b_mn_major || bn % 128 == 0) && !(p.debug & 2)) ? 1 : 0;
   }
-  CUtensorMap ta, tb;
-  int rc;
-  // K-major operand: global [rows, K]; MN-major operand: global [K, rows].
-  rc = a_mn_major ? make_tmap(&ta, A, K, M, lda, 64, 64) : make_tmap(&ta, A, M, K, lda, 64, BM);
-  if (rc) return rc;
-  rc = b_mn_major ? make_tmap(&tb, B, K, N, ldb, 64, 64) : make_tmap(&tb, B, N, K, ldb, 64, p.pair ? bn / 2 : bn);
-  if (rc) return rc;
-  // epilogue tiles: 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), stored / reduced / loaded by TMA
-  EpiMaps em;
-  memset(&em, 0, sizeof(em));
-  if (epi != FC_EPI_PATCH) {
-    const int out16 = (epi == FC_EPI_BF16 || epi == FC_EPI_GELU || epi == FC_EPI_MULAUX);
-    FC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out16 ? 2 : 4)) % 16 == 0,
-               "fc_gemm_bf16: output must be 16-byte aligned with a 16-byte multiple row pitch");
-    rc = make_tmap(&em.o, out, M, N, ldo, out16 ? 64 : 32, 32, !out16);
+  AllMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int out16 = (epi == FC_EPI_BF16 || epi == FC_EPI_GELU || epi == FC_EPI_MULAUX);
+  for (int g = 0; g < groups; ++g) {
+    GroupMaps& gm = maps.g[g];
+    int rc;
+    // K-major operand: global [rows, K]; MN-major operand: global [K, rows].
+    rc = a_mn_major ? make_tmap(&gm.a, A[g], K, M, lda, 64, 64) : make_tmap(&gm.a, A[g], M, K, lda, 64, BM);
     if (rc) return rc;
-    if (epi == FC_EPI_GELU) {
-      rc = make_tmap(&em.o2, out2, M, N, ldo, 64, 32, 0);
+    rc = b_mn_major ? make_tmap(&gm.b, B[g], K, N, ldb, 64, 64) : make_tmap(&gm.b, B[g], N, K, ldb, 64, p.pair ? bn / 2 : bn);
+    if (rc) return rc;
+    // epilogue tiles: 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), stored / reduced / loaded by TMA
+    if (epi != FC_EPI_PATCH) {
+      FC_REQUIRE((reinterpret_cast<uintptr_t>(out[g]) & 15) == 0 && (ldo * (out16 ? 2 : 4)) % 16 == 0,
+                 "fc_gemm_bf16: output must be 16-byte aligned with a 16-byte multiple row pitch");
+      rc = make_tmap(&gm.o, out[g], M, N, ldo, out16 ? 64 : 32, 32, !out16);
       if (rc) return rc;
-    }
-    if (epi == FC_EPI_RESID) {
-      rc = make_tmap(&em.r, resid, M, N, ldo, 32, 32, 1);
-      if (rc) return rc;
-    }
-    if (epi == FC_EPI_MULAUX) {
-      rc = make_tmap(&em.r, aux, M, N, ldo, 64, 32, 0);
-      if (rc) return rc;
+      if (epi == FC_EPI_GELU) {
+        rc = make_tmap(&gm.o2, out2[g], M, N, ldo, 64, 32, 0);
+        if (rc) return rc;
+      }
+      if (epi == FC_EPI_RESID) {
+        rc = make_tmap(&gm.r, resid[g], M, N, ldo, 32, 32, 1);
+        if (rc) return rc;
+      }
+      if (epi == FC_EPI_MULAUX) {
+        rc = make_tmap(&gm.r, aux[g], M, N, ldo, 64, 32, 0);
+        if (rc) return rc;
+      }
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int am = a_mn_major ? 1 : 0, bm = b_mn_major ? 1 : 0;
   if (p.pair) {
-    if (bn == 256) return launch_bn<256, 1>(ta, tb, em, p, am, bm, device, st);
-    if (bn == 192) return launch_bn<192, 1>(ta, tb, em, p, am, bm, device, st);
-    return launch_bn<128, 1>(ta, tb, em, p, am, bm, device, st);
+    if (bn == 256) return launch_bn<256, 1>(maps, p, am, bm, device, st);
+    if (bn == 192) return launch_bn<192, 1>(maps, p, am, bm, device, st);
+    return launch_bn<128, 1>(maps, p, am, bm, device, st);
   }
-  if (bn == 256) return launch_bn<256, 0>(ta, tb, em, p, am, bm, device, st);
-  if (bn == 192) return launch_bn<192, 0>(ta, tb, em, p, am, bm, device, st);
-  return launch_bn<128, 0>(ta, tb, em, p, am, bm, device, st);
+  if (bn == 256) return launch_bn<256, 0>(maps, p, am, bm, device, st);
+  if (bn == 192) return launch_bn<192, 0>(maps, p, am, bm, device, st);
+  return launch_bn<128, 0>(maps, p, am, bm, device, st);
+}
+
+// One operand set: the plain GEMM (ref: every F.linear of the reference's Block).
+extern "C" int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_major, const void* B,
+                            long long ldb, int b_mn_major, int epi, void* out, void* out2, long long ldo,
+                            const float* bias, const float* resid, const float* row_scale, int rows_per_group,
+                            const void* aux, const float* pos, int patches, float alpha, int splits,
+                            float* colsum, int device, void* stream) {
+  FC_REQUIRE(M > 0 && N > 0 && K > 0, "fc_gemm_bf16: empty problem %d %d %d", M, N, K);
+  FC_REQUIRE(out != nullptr, "fc_gemm_bf16: null output");
+  return fc_gemm_bf16_grouped(1, M, N, K, &A, lda, a_mn_major, &B, ldb, b_mn_major, epi, &out, &out2, ldo, &bias, &resid,
+                              &row_scale, rows_per_group, &aux, &pos, patches, alpha, splits, &colsum, device, stream);
 }

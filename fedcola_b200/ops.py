@@ -47,6 +47,36 @@ def gemm_bf16(A, B, epi, out, *, a_mn=False, b_mn=False, out2=None, bias=None, r
     return out
 
 
+def _ptr_table(ts):
+    """host array of device pointers (None -> NULL table)"""
+    import ctypes
+    if ts is None:
+        return None
+    return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+
+def gemm_bf16_grouped(As, Bs, epi, outs, *, a_mn=False, b_mn=False, out2s=None, biases=None, resids=None,
+                      row_scales=None, rows_per_group=0, auxs=None, poss=None, patches=0, alpha=1.0, splits=1, colsums=None):
+    """The same GEMM for len(As) independent operand sets (same shapes / strides) in ONE launch (fc_gemm_bf16_grouped)."""
+    G = len(As)
+    A, B, out = As[0], Bs[0], outs[0]
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N = B.shape[1] if b_mn else B.shape[0]
+    for a, b, o in zip(As, Bs, outs):
+        assert a.shape == A.shape and b.shape == B.shape and o.shape == out.shape
+        assert a.stride() == A.stride() and b.stride() == B.stride() and o.stride() == out.stride()
+    dev = _dev(A)
+    ldo = out.stride(0) if epi != EPI_PATCH else out.shape[-1]
+    rc = _lib.lib().fc_gemm_bf16_grouped(c_int(G), c_int(M), c_int(N), c_int(K), _ptr_table(As), c_ll(A.stride(0)),
+                                         c_int(int(a_mn)), _ptr_table(Bs), c_ll(B.stride(0)), c_int(int(b_mn)), c_int(epi),
+                                         _ptr_table(outs), _ptr_table(out2s), c_ll(ldo), _ptr_table(biases),
+                                         _ptr_table(resids), _ptr_table(row_scales), c_int(rows_per_group), _ptr_table(auxs),
+                                         _ptr_table(poss), c_int(patches), c_f(alpha), c_int(splits), _ptr_table(colsums),
+                                         c_int(dev), _lib.stream_ptr(A.device))
+    _lib.check(rc, "fc_gemm_bf16_grouped")
+    return outs
+
+
 def _st(t):
     return _lib.stream_ptr(t.device)
 
@@ -67,6 +97,25 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, dbias=None):
                                      c_int(64), c_int(_dev(qkv)), _st(qkv))
     _lib.check(rc, "fc_attention_bwd")
     return dqkv
+
+
+def attention_fwd_grouped(qkvs, B, N, H):
+    """The same attention for several clients' qkv tensors in ONE launch (fc_attention_fwd_grouped)."""
+    outs = [torch.empty(B, N, H * 64, dtype=torch.bfloat16, device=q.device) for q in qkvs]
+    lses = [torch.empty(B, H, N, dtype=torch.float32, device=q.device) for q in qkvs]
+    rc = _lib.lib().fc_attention_fwd_grouped(c_int(len(qkvs)), _ptr_table(qkvs), _ptr_table(outs), _ptr_table(lses), c_int(B),
+                                             c_int(N), c_int(H), c_int(64), c_int(_dev(qkvs[0])), _st(qkvs[0]))
+    _lib.check(rc, "fc_attention_fwd_grouped")
+    return outs, lses
+
+
+def attention_bwd_grouped(qkvs, outs, douts, lses, B, N, H, dbiases=None):
+    dqkvs = [torch.empty_like(q) for q in qkvs]
+    rc = _lib.lib().fc_attention_bwd_grouped(c_int(len(qkvs)), _ptr_table(qkvs), _ptr_table(outs), _ptr_table(douts),
+                                             _ptr_table(lses), _ptr_table(dqkvs), _ptr_table(dbiases), c_int(B), c_int(N),
+                                             c_int(H), c_int(64), c_int(_dev(qkvs[0])), _st(qkvs[0]))
+    _lib.check(rc, "fc_attention_bwd_grouped")
+    return dqkvs
 
 
 def layernorm_fwd(x, gamma, beta, eps, bf16_out=True):

@@ -379,8 +379,13 @@ class ClientTrainer:
         self.args = a
         rt.refresh_operands()
 
-    def step(self, img, ids, labels, loss_kind, droppath=None):
+    def prepare(self, img, ids, labels, loss_kind, droppath=None):
+        """Fill the native argument block for one batch (no launch). Returns the batch size."""
         rt, a, p = self.rt, self.args, self.rt.plan
+        for t, dt, name in ((img, torch.float32, "images"), (ids, torch.int64, "token ids"), (labels, torch.int64, "labels")):
+            if t is not None and (t.dtype != dt or not t.is_contiguous() or not t.is_cuda):
+                raise TypeError(f"fedcola_b200: {name} must be a contiguous CUDA {dt} tensor (got {t.dtype}, "
+                                f"contiguous={t.is_contiguous()}, device={t.device}): the kernels read raw pointers")
         B = (img if img is not None else ids).shape[0]
         self.step_count += 1
         a.B, a.loss_kind, a.step = B, loss_kind, self.step_count
@@ -401,6 +406,27 @@ class ClientTrainer:
         a.n_prep_layers, a.n_prep_tiles = len(p.prep_table), p.n_prep_tiles
         a.aux_layers = rt.aux_dev.data_ptr() if rt.aux_dev is not None else None
         a.n_aux_layers, a.n_aux_chunks = len(p.aux_table), p.n_aux_chunks
-        rc = _lib.lib().fc_client_step(ctypes.byref(p.desc), ctypes.byref(a), c_int(rt.dev_index),
-                                       _lib.stream_ptr(rt.device))
-        _lib.check(rc, "fc_client_step")
+        self._keep = (img, ids, labels, droppath)      # the launch is asynchronous: keep the batch alive
+        return B
+
+    def step(self, img, ids, labels, loss_kind, droppath=None):
+        self.prepare(img, ids, labels, loss_kind, droppath)
+        group_step([self])
+
+
+MAX_GROUP = 4          # FC_STEP_MAX_GROUPS
+
+
+def group_step(trainers):
+    """ONE native call trains one batch of every trainer of a lockstep group (fc_client_step_group): all trainers hold
+    the same model architecture on the same device and were `prepare`d with batches of the same size."""
+    t0 = trainers[0]
+    if not 1 <= len(trainers) <= MAX_GROUP:
+        raise ValueError(f"a lockstep group holds 1..{MAX_GROUP} clients")
+    for t in trainers[1:]:
+        if t.rt.plan is not t0.rt.plan or t.rt.device != t0.rt.device or t.args.B != t0.args.B:
+            raise ValueError("clients of a lockstep group must share the model architecture, the device and the batch size")
+    arr = (ctypes.POINTER(StepArgs) * len(trainers))(*[ctypes.pointer(t.args) for t in trainers])
+    rc = _lib.lib().fc_client_step_group(ctypes.byref(t0.rt.plan.desc), c_int(len(trainers)), arr, c_int(t0.rt.dev_index),
+                                         _lib.stream_ptr(t0.rt.device))
+    _lib.check(rc, "fc_client_step_group")

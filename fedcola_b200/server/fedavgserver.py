@@ -305,33 +305,50 @@ class FedavgServer(BaseServer):
                 return None
             raise NotImplementedError("client-side evaluation is dead code in the reference (fedavgclient.py:118)")
 
-        def update_client(client):
-            dev = torch.device(client.device)
-            with torch.cuda.device(dev), torch.cuda.stream(torch.cuda.Stream(dev)):
-                if client.model is None:
-                    client.download(self.global_models)
-                client.args.lr = self.curr_lr
-                if self.args.freeze_modality != "none" and client.modality == self.args.freeze_modality:
-                    hi = self.args.freeze_rounds + self.args.warmup_rounds
-                    if self.args.warmup_rounds < self.round <= hi:
-                        self._freeze_shared_params(client)
-                    elif self.round > hi:
-                        self._unfreeze_params(client)
-                result = client.update()
-                torch.cuda.current_stream().synchronize()
-            if not retain_model:
-                client.model = None
-            return {client.id: len(client.training_set)}, {client.id: result}
+        def prepare(client):
+            if client.model is None:
+                client.download(self.global_models)
+            client.args.lr = self.curr_lr
+            if self.args.freeze_modality != "none" and client.modality == self.args.freeze_modality:
+                hi = self.args.freeze_rounds + self.args.warmup_rounds
+                if self.args.warmup_rounds < self.round <= hi:
+                    self._freeze_shared_params(client)
+                elif self.round > hi:
+                    self._unfreeze_params(client)
+
+        def update_group(group):
+            """One worker = one lockstep group of clients (same GPU, same global model): their batches are trained
+            by shared kernel launches (client/fedavgclient.py::update_group).  A group of one is the reference's
+            per-client worker (:506-519)."""
+            from ..client.fedavgclient import update_group as run
+            dev = torch.device(group[0].device)
+            stream = self._take_stream(dev)
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(stream):
+                    for client in group:
+                        prepare(client)
+                    res = run(group)
+                    stream.synchronize()
+            finally:
+                self._stream_pool[str(dev)].put(stream)
+            out = []
+            for client in group:
+                if not retain_model:
+                    client.model = None
+                out.append(({client.id: len(client.training_set)}, {client.id: res[client.id]}))
+            return out
 
         torch.cuda.synchronize(self.server_device)       # the global arenas the clients copy from are final
-        local = [i for i in ids if self._owner.get(i, 0) == self.rank]
+        local = [self.clients[i] for i in ids if self._owner.get(i, 0) == self.rank]
+        groups = self._lockstep_groups(local)
         results = []
-        if self.args.num_thread > 1 and len(local) > 1:
+        if self.args.num_thread > 1 and len(groups) > 1:
             with concurrent.futures.ThreadPoolExecutor(max_workers=self.args.num_thread) as pool:
-                for fut in concurrent.futures.as_completed([pool.submit(update_client, self.clients[i]) for i in local]):
-                    results.append(fut.result())
+                for fut in concurrent.futures.as_completed([pool.submit(update_group, g) for g in groups]):
+                    results.extend(fut.result())
         else:
-            results = [update_client(self.clients[i]) for i in local]
+            for g in groups:
+                results.extend(update_group(g))
         d = _dist()
         if d is not None:        # every rank logs the whole round: exchange the per-client epoch statistics
             results = self._exchange_results(d, ids, results)
@@ -347,6 +364,36 @@ class FedavgServer(BaseServer):
         self.results[self.round]["clients_updated"] = self._log_results(sizes, res, eval=False, participated=True,
                                                                         save_raw=False)
         return sizes
+
+    def _take_stream(self, dev):
+        """A worker's CUDA stream, from a small per-device pool that lives as long as the server: torch's caching
+        allocator keeps one block pool per stream, so re-using the same few streams every round lets every multi-GB
+        activation workspace be served from cache (a fresh stream per worker meant fresh cudaMallocs every round)."""
+        import queue
+        pools = self.__dict__.setdefault("_stream_pool", {})
+        q = pools.get(str(dev))
+        if q is None:
+            q = pools[str(dev)] = queue.Queue()
+            for _ in range(max(1, int(self.args.num_thread))):
+                q.put(torch.cuda.Stream(dev))
+        return q.get()
+
+    def _lockstep_groups(self, clients):
+        """Partition this rank's sampled clients into lockstep groups: same GPU, same global model (dataset) — i.e. the
+        same architecture and batch size — at most `args.client_group` (default 3, limit 4) per group, in id order.
+        `args.client_group = 1` trains every client on its own, as the reference's workers do."""
+        from .. import runtime as R
+        size = int(getattr(self.args, "client_group", 3))
+        size = max(1, min(size, R.MAX_GROUP))
+        buckets = {}
+        for c in clients:
+            buckets.setdefault((c.device, c.dataset), []).append(c)
+        groups = []
+        for members in buckets.values():
+            for k in range(0, len(members), size):
+                groups.append(members[k:k + size])
+        groups.sort(key=lambda g: g[0].id)
+        return groups
 
     def _exchange_results(self, d, ids, results):
         """All ranks end with every sampled client's {epoch: {loss, metrics}}: one fixed-size all-reduce of a

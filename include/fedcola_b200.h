@@ -100,6 +100,19 @@ int fc_gemm_bf16(int M, int N, int K, const void* A, long long lda, int a_mn_maj
                  const void* aux, const float* pos, int patches, float alpha, int splits, float* colsum,
                  int device, void* stream);
 
+/* The same GEMM (shape, strides, majors, epilogue) for `groups` (<= FC_GEMM_MAX_GROUPS) independent operand sets in ONE
+ * launch — the same layer of several clients that train in lockstep (ref: the ThreadPoolExecutor of
+ * src/server/fedavgserver.py:566-577 runs these clients side by side, one kernel stream each).  Every pointer
+ * argument of fc_gemm_bf16 becomes a host array of `groups` pointers (optional operands: a NULL table or NULL entries,
+ * consistently across groups). */
+#define FC_GEMM_MAX_GROUPS 4
+int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void* const* A, long long lda, int a_mn_major,
+                         const void* const* B, long long ldb, int b_mn_major, int epi, void* const* out,
+                         void* const* out2, long long ldo, const float* const* bias, const float* const* resid,
+                         const float* const* row_scale, int rows_per_group, const void* const* aux,
+                         const float* const* pos, int patches, float alpha, int splits, float* const* colsum,
+                         int device, void* stream);
+
 /* Per-launch GEMM timing with CUDA events on the launching stream (measurement aid; off by default). */
 void fc_gemm_profile(int enable);
 long long fc_gemm_profile_collect(double* total_ms, double* total_flops);
@@ -115,6 +128,14 @@ int fc_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H
  * left untouched — it is identically zero because softmax is invariant to a shift of the scores */
 int fc_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv,
                      float* dbias, int B, int N, int H, int head_dim, int device, void* stream);
+/* The same attention for `groups` (<= FC_ATTN_MAX_GROUPS) clients' tensors of one shape in ONE launch (lockstep client
+ * groups, see fc_gemm_bf16_grouped): every tensor argument becomes a host array of `groups` pointers. */
+#define FC_ATTN_MAX_GROUPS 4
+int fc_attention_fwd_grouped(int groups, const void* const* qkv, void* const* out, float* const* lse, int B, int N,
+                             int H, int head_dim, int device, void* stream);
+int fc_attention_bwd_grouped(int groups, const void* const* qkv, const void* const* out, const void* const* d_out,
+                             const float* const* lse, void* const* dqkv, float* const* dbias, int B, int N, int H,
+                             int head_dim, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the fp32 residual stream           ref: src/models/mome.py:203,215,226-227,751-752
@@ -131,6 +152,19 @@ int fc_layernorm_bwd(const void* dy, int dy_is_bf16, long long dy_row_stride, co
                      float* dx, long long dx_row_stride, int accumulate, void* dxs_bf16,
                      long long dxs_row_stride, const float* row_scale, int rows_per_group, float* dgamma,
                      float* dbeta, float* dxs_colsum, int rows, int d, int device, void* stream);
+
+/* Grouped forms (lockstep client groups, see fc_gemm_bf16_grouped): every tensor argument becomes a host array of
+ * `groups` (<= FC_LN_MAX_GROUPS) pointers; shapes / strides are shared. */
+#define FC_LN_MAX_GROUPS 4
+int fc_layernorm_fwd_grouped(int groups, const float* const* x, long long x_row_stride, const float* const* gamma,
+                             const float* const* beta, float eps, void* const* y_bf16, float* const* y_f32,
+                             float* const* mean, float* const* rstd, int rows, int d, int device, void* stream);
+int fc_layernorm_bwd_grouped(int groups, const void* const* dy, int dy_is_bf16, long long dy_row_stride,
+                             const float* const* x, long long x_row_stride, const float* const* mean,
+                             const float* const* rstd, const float* const* gamma, float* const* dx,
+                             long long dx_row_stride, int accumulate, void* const* dxs_bf16, long long dxs_row_stride,
+                             const float* const* row_scale, int rows_per_group, float* const* dgamma,
+                             float* const* dbeta, float* const* dxs_colsum, int rows, int d, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embeddings / heads / losses        ref: src/models/mome.py:597-611 (image), :632-639 (text, BertEmbeddings),
@@ -262,6 +296,13 @@ typedef struct {
 } fc_step_args;
 
 int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int device, void* stream);
+/* The same step for a lockstep group of `n` (<= FC_STEP_MAX_GROUPS) clients of ONE model architecture at one batch size:
+ * every GEMM / attention / LayerNorm launch of the step covers all of them (fc_*_grouped), so the fixed cost of a
+ * launch — prologue, first-load latency, exposed last epilogue, wave quantisation: 40-50 % of a ViT-S GEMM at B=112 —
+ * is paid once per group.  ref: the clients the reference's ThreadPoolExecutor trains side by side
+ * (src/server/fedavgserver.py:566-577), each running src/client/fedavgclient.py:79-102. */
+#define FC_STEP_MAX_GROUPS 4
+int fc_client_step_group(const fc_mat_desc* m, int n, const fc_step_args* const* args, int device, void* stream);
 
 /* struct-layout handshake for FFI bindings */
 int fc_sizeof_mat_desc(void);

@@ -235,3 +235,43 @@ def test_droppath_scales_are_applied(cuda):
     vals = torch.unique(m[0, 1]).tolist()
     assert torch.all(m[0, 0] == 1) and all(min(abs(v), abs(v - 1 / 0.7)) < 1e-6 for v in vals)
     assert R.droppath_scales(spec, 64, cuda, False) is None
+
+
+@pytest.mark.parametrize("kind,opt", [("img_aux", "SGD"), ("txt", "SGD"), ("pair", "SGD"), ("txt_aux", "AdamW")])
+def test_lockstep_group_equals_separate_clients(kind, opt, cuda):
+    """fc_client_step_group: three clients of one architecture (different weights, different batches) trained in
+    lockstep — every GEMM / attention / LayerNorm launch shared — end exactly where three separate fc_client_step
+    sequences end (up to the fp32 reordering of the split-K / bias-gradient atomics)."""
+    size = dict(embed_dim=128, depth=3, num_heads=2)
+    ds, _ = H.TRAIN_KINDS[kind]
+    m = H.DS_MODALITY[ds]
+    lk = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}[m]
+    runs = {}
+    for mode in ("separate", "group"):
+        models = [build_model(kind, cuda, size=size, seed=7 + g)[0] for g in range(3)]
+        trainers = [R.ClientTrainer(mm, optimizer=opt, lr=1e-3 if opt == "AdamW" else 0.05, momentum=0.9 if opt == "SGD" else 0.0,
+                                    max_grad_norm=1.0) for mm in models]
+        data = [H.make_samples(ds, 12, 50 + g) for g in range(3)]
+        for s0 in range(0, 12, 6):
+            batch = []
+            for g in range(3):
+                a, b = data[g][0][s0:s0 + 6].to(cuda).contiguous(), data[g][1][s0:s0 + 6].to(cuda).contiguous()
+                batch.append((a, None, b) if m == "img" else (None, a, b) if m == "txt" else (a, b, None))
+            if mode == "separate":
+                for t, x in zip(trainers, batch):
+                    t.step(*x, lk)
+            else:
+                for t, x in zip(trainers, batch):
+                    t.prepare(*x, lk)
+                R.group_step(trainers)
+        torch.cuda.synchronize()
+        runs[mode] = ([mm.arena.clone() for mm in models], [t.stats.clone() for t in trainers])
+    for g in range(3):
+        a, b = runs["separate"][0][g], runs["group"][0][g]
+        if opt == "SGD":         # linear in the gradients: only the fp32 reordering of the atomics remains
+            assert (a - b).norm() <= 1e-5 * a.norm(), (g, ((a - b).norm() / a.norm()).item())
+        else:                    # Adam divides by |g|: where g ~ 0 a reordered sum flips the sign of a full-size step
+            assert (a - b).abs().max().item() <= 2.1 * 1e-3 * 2, g
+            assert ((a - b).abs() > 1e-6).float().mean().item() < 0.02, g
+        assert torch.allclose(runs["separate"][1][g], runs["group"][1][g], rtol=1e-4, atol=1e-5)
+    assert not torch.equal(runs["group"][0][0], runs["group"][0][1])            # the clients really differ

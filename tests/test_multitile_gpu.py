@@ -170,3 +170,84 @@ def test_attention_many_items_per_cta(B, N, H, cap, cuda):
 def test_attention_bench_shapes(B, N, H, cuda):
     """The bench's own launches: 672 (ViT-S) / 1 152 (ViT-B) items over 148 SMs."""
     _attn_check(B, N, H, cuda, seed=9)
+
+
+# ---- lockstep client groups: one launch for several clients' operands ------------------------------------
+@pytest.mark.parametrize("cap", [0, 5])
+@pytest.mark.parametrize("a_mn,b_mn,epi", [(0, 0, ops.EPI_BF16), (0, 0, ops.EPI_GELU), (0, 0, ops.EPI_RESID),
+                                           (0, 1, ops.EPI_MULAUX), (1, 1, ops.EPI_ATOMIC_F32)])
+def test_grouped_gemm_equals_single_launches(a_mn, b_mn, epi, cap, cuda):
+    """fc_gemm_bf16_grouped over 3 operand sets == 3 single launches, bit for bit (the split-K accumulation: to fp32
+    reordering), including with many tiles per CTA."""
+    G, M, N, K = 3, 1000, 768, 384
+    As = [_mk(K, M, cuda, 100 + g, 0.5) if a_mn else _mk(M, K, cuda, 100 + g, 0.5) for g in range(G)]
+    Bs = [_mk(K, N, cuda, 200 + g, 0.1) if b_mn else _mk(N, K, cuda, 200 + g, 0.1) for g in range(G)]
+    biases = [torch.randn(N, device=cuda) * 0.1 for _ in range(G)]
+    kw1, kwg = {}, {}
+    if epi in (ops.EPI_BF16, ops.EPI_GELU, ops.EPI_MULAUX):
+        mk_out = lambda: torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)     # noqa: E731
+    else:
+        mk_out = lambda: torch.ones(M, N, device=cuda)                            # noqa: E731
+    single, grouped = [mk_out() for _ in range(G)], [mk_out() for _ in range(G)]
+    extra_s, extra_g = [None] * G, None
+    if epi == ops.EPI_GELU:
+        extra_s, extra_g = [mk_out() for _ in range(G)], [mk_out() for _ in range(G)]
+    resid = [torch.randn(M, N, device=cuda) for _ in range(G)]
+    aux = [_mk(M, N, cuda, 300 + g) for g in range(G)]
+    cs_s, cs_g = [torch.zeros(N, device=cuda) for _ in range(G)], [torch.zeros(N, device=cuda) for _ in range(G)]
+    with ops.grid_cap(cap):
+        for g in range(G):
+            kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn))
+            if epi in (ops.EPI_BF16, ops.EPI_GELU, ops.EPI_RESID):
+                kw["bias"] = biases[g]
+            if epi == ops.EPI_GELU:
+                kw["out2"] = extra_s[g]
+            if epi == ops.EPI_RESID:
+                kw["resid"] = resid[g]
+            if epi == ops.EPI_MULAUX:
+                kw.update(aux=aux[g], colsum=cs_s[g])
+            if epi == ops.EPI_ATOMIC_F32:
+                kw.update(splits=3, alpha=0.5)
+            ops.gemm_bf16(As[g], Bs[g], epi, single[g], **kw)
+        kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn))
+        if epi in (ops.EPI_BF16, ops.EPI_GELU, ops.EPI_RESID):
+            kw["biases"] = biases
+        if epi == ops.EPI_GELU:
+            kw["out2s"] = extra_g
+        if epi == ops.EPI_RESID:
+            kw["resids"] = resid
+        if epi == ops.EPI_MULAUX:
+            kw.update(auxs=aux, colsums=cs_g)
+        if epi == ops.EPI_ATOMIC_F32:
+            kw.update(splits=3, alpha=0.5)
+        ops.gemm_bf16_grouped(As, Bs, epi, grouped, **kw)
+    torch.cuda.synchronize()
+    for g in range(G):
+        if epi == ops.EPI_ATOMIC_F32:
+            _close(grouped[g], single[g], 1e-5, 1e-5, f"group {g}")
+        else:
+            assert torch.equal(grouped[g], single[g]), f"group {g}"
+        if epi == ops.EPI_GELU:
+            assert torch.equal(extra_g[g], extra_s[g])
+        if epi == ops.EPI_MULAUX:
+            _close(cs_g[g], cs_s[g], 1e-5, 1e-4, f"colsum {g}")
+
+
+@pytest.mark.parametrize("cap", [0, 3])
+@pytest.mark.parametrize("B,N,H", [(5, 197, 3), (7, 64, 6), (4, 16, 2)])
+def test_grouped_attention_equals_single_launches(B, N, H, cap, cuda):
+    G = 3
+    torch.manual_seed(5)
+    qkvs = [torch.randn(B, N, 3, H, 64, device=cuda).to(torch.bfloat16) for _ in range(G)]
+    douts = [(torch.randn(B, N, H * 64, device=cuda) * 0.1).to(torch.bfloat16) for _ in range(G)]
+    with ops.grid_cap(cap):
+        outs, lses = ops.attention_fwd_grouped(qkvs, B, N, H)
+        dbg = [torch.zeros(3 * H * 64, device=cuda) for _ in range(G)]
+        dqkvs = ops.attention_bwd_grouped(qkvs, outs, douts, lses, B, N, H, dbiases=dbg)
+        for g in range(G):
+            o, l = ops.attention_fwd(qkvs[g], B, N, H)
+            db = torch.zeros(3 * H * 64, device=cuda)
+            dq = ops.attention_bwd(qkvs[g], o, douts[g], l, B, N, H, dbias=db)
+            assert torch.equal(o, outs[g]) and torch.equal(l, lses[g]), f"forward, group {g}"
+            assert torch.equal(dq, dqkvs[g]), f"backward, group {g}"
+            _close(dbg[g], db, 1e-5, 1e-5 * (B * N) ** 0.5, f"bias gradient, group {g}")
