@@ -5,8 +5,10 @@
 // following tcgen05 GEMM consumes; the backward adds into the running residual gradient and also emits the
 // DropPath-scaled bf16 copy that the next backward GEMM consumes, so no separate cast/scale kernel runs.
 #include "common.cuh"
+#include "sm100.cuh"
 #include "../../include/fedcola_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -212,6 +214,193 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ Bwd
   }
 }
 
+// ---- backward, streamed through shared memory ------------------------------------------------------------
+// The register version above keeps one row per warp in flight (111 registers -> 16 warps per SM): ~35 KB of loads
+// outstanding per SM, 3.7 TB/s on the 66 k-row launches of a client group.  Here a producer warp streams the rows
+// — dy, x and the running dx of 8 rows per stage — into a 5-stage shared-memory ring with 1-D bulk copies
+// (cp.async.bulk + mbarrier transaction counts), so ~150 KB are in flight per SM whatever the consumers' register
+// budget is; the 8 consumer warps (one row each per stage) read the row from shared memory, reduce, and store dx /
+// dxs straight to global memory.  Same arithmetic, same order of operations per row as the register version.
+constexpr int kRingRows = 8;           // rows per stage == consumer warps
+constexpr int kRingThreads = (kRingRows + 1) * 32;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(sm100::smem_u32(bar)) : "memory");
+}
+
+template <int NV, bool DY_BF16>
+__global__ void __launch_bounds__(kRingThreads, (NV <= 3 ? 2 : 1))
+ln_bwd_ring_kernel(const __grid_constant__ BwdSets S, long long dy_row_stride, long long x_row_stride,
+                   long long dx_row_stride, int accumulate, long long dxs_row_stride, int rows_per_group, int rows,
+                   int d, int stages) {
+  using namespace sm100;
+  extern __shared__ __align__(128) uint8_t ring[];
+  const BwdSet& A = S.g[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = d >> 2;
+  const int dy_bytes = d * (DY_BF16 ? 2 : 4), f_bytes = d * 4;
+  const int row_bytes = dy_bytes + f_bytes + (accumulate ? f_bytes : 0);      // dy | x | dx (16-byte multiples: d % 8 == 0)
+  const int stage_bytes = kRingRows * row_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  float* s_part = reinterpret_cast<float*>(ring);                              // reused after the ring has drained
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kRingRows);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int n_chunks = (rows + kRingRows - 1) / kRingRows;
+
+  if (warp == kRingRows) {
+    // ================= producer warp: lane l copies the three pieces of row l % 8 =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+      const int row0 = chunk * kRingRows;
+      const int nrows = min(kRingRows, rows - row0);
+      if (lane == 0) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], nrows * row_bytes);
+      }
+      __syncwarp();
+      const int r = lane & 7, piece = lane >> 3;          // piece 0: dy, 1: x, 2: running dx
+      if (r < nrows && piece < (accumulate ? 3 : 2)) {
+        const size_t row = row0 + r;
+        const uint32_t dst = smem_u32(ring + s * stage_bytes + r * row_bytes);
+        if (piece == 0) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(A.dy) + row * dy_row_stride * (DY_BF16 ? 2 : 4);
+          bulk_g2s(dst, src, dy_bytes, &full[s]);
+        } else if (piece == 1) {
+          bulk_g2s(dst + dy_bytes, A.x + row * x_row_stride, f_bytes, &full[s]);
+        } else {
+          bulk_g2s(dst + dy_bytes + f_bytes, A.dx + row * dx_row_stride, f_bytes, &full[s]);
+        }
+      }
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // ================= consumer warps: warp w owns row w of every stage =================
+    float4 dg[NV], db[NV], dc[NV], gm[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      dg[i] = db[i] = dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = lane + i * 32;
+      gm[i] = c < nvec ? __ldg(reinterpret_cast<const float4*>(A.gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+      const int row = chunk * kRingRows + warp;
+      const bool live = row < rows;                       // warp-uniform
+      float m = 0.f, r = 0.f, sc = 1.0f;
+      if (live) {                                         // issued before the wait: latency hides behind it
+        m = __ldg(A.mean + row);
+        r = __ldg(A.rstd + row);
+        if (A.row_scale) sc = __ldg(A.row_scale + row / rows_per_group);
+      }
+      mbar_wait(&full[s], ph);
+      if (live) {
+        const uint8_t* base = ring + s * stage_bytes + warp * row_bytes;
+        const float4* xs = reinterpret_cast<const float4*>(base + dy_bytes);
+        const float4* ps = reinterpret_cast<const float4*>(base + dy_bytes + f_bytes);
+        float4 g[NV], xh[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + i * 32;
+          if (c < nvec) {
+            float4 dyv;
+            if (DY_BF16) {
+              const uint2 raw = reinterpret_cast<const uint2*>(base)[c];
+              const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+              const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+              dyv = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              dyv = reinterpret_cast<const float4*>(base)[c];
+            }
+            const float4 xv = xs[c];
+            xh[i] = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
+            g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
+            s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+            dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
+            db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
+          }
+        }
+        // the two row reductions share their shuffle rounds
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 / d, m2 = s2 / d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + i * 32;
+          if (c < nvec) {
+            float4 o;
+            o.x = r * (g[i].x - m1 - xh[i].x * m2);
+            o.y = r * (g[i].y - m1 - xh[i].y * m2);
+            o.z = r * (g[i].z - m1 - xh[i].z * m2);
+            o.w = r * (g[i].w - m1 - xh[i].w * m2);
+            if (accumulate) {
+              const float4 pv = ps[c];
+              o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+            }
+            reinterpret_cast<float4*>(A.dx + (size_t)row * dx_row_stride)[c] = o;
+            if (A.dxs) {
+              const uint32_t w0 = pack2(o.x * sc, o.y * sc), w1 = pack2(o.z * sc, o.w * sc);
+              reinterpret_cast<uint2*>(A.dxs + (size_t)row * dxs_row_stride)[c] = make_uint2(w0, w1);
+              if (A.dxs_colsum) {
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+                dc[i].x += a.x; dc[i].y += a.y; dc[i].z += b.x; dc[i].w += b.y;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);              // this warp has finished reading its row of the stage
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+    // per-warp column partials -> shared memory (the ring is free once every consumer warp is past its last stage)
+    asm volatile("bar.sync 1, %0;" ::"n"(kRingRows * 32) : "memory");
+    if (A.dgamma != nullptr || A.dxs_colsum != nullptr) {
+      float* pg = s_part;
+      float* pb = s_part + kRingRows * d;
+      float* pc = s_part + 2 * kRingRows * d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          reinterpret_cast<float4*>(pg + warp * d)[c] = dg[i];
+          reinterpret_cast<float4*>(pb + warp * d)[c] = db[i];
+          reinterpret_cast<float4*>(pc + warp * d)[c] = dc[i];
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kRingRows * 32) : "memory");
+      for (int c = threadIdx.x; c < d; c += kRingRows * 32) {
+        float a = 0.f, b = 0.f, e = 0.f;
+        for (int w = 0; w < kRingRows; ++w) {
+          a += pg[w * d + c];
+          b += pb[w * d + c];
+          e += pc[w * d + c];
+        }
+        if (A.dgamma != nullptr) {
+          atomicAdd(A.dgamma + c, a);
+          atomicAdd(A.dbeta + c, b);
+        }
+        if (A.dxs_colsum != nullptr) atomicAdd(A.dxs_colsum + c, e);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int fc_layernorm_fwd_grouped(int groups, const float* const* x, long long x_row_stride,
@@ -275,6 +464,54 @@ extern "C" int fc_layernorm_bwd_grouped(int groups, const void* const* dy, int d
                "fc_layernorm_bwd: groups disagree on optional operands");
     S.g[g] = BwdSet{dy[g], x[g], mean[g], rstd[g], gamma[g], dx[g], reinterpret_cast<__nv_bfloat16*>(at(dxs_bf16, g)),
                     at(row_scale, g), at(dgamma, g), at(dbeta, g), at(dxs_colsum, g)};
+  }
+  cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // streamed version: rows must be 16-byte aligned pieces (d % 8 == 0, aligned strides and bases) and the launch big
+    // enough to fill the ring; FC_LN_RING=0 switches it off (measurement aid)
+    static const int use_ring = getenv("FC_LN_RING") ? atoi(getenv("FC_LN_RING")) : 1;
+    const int esz = dy_is_bf16 ? 2 : 4;
+    bool ok = use_ring && d % 8 == 0 && (dy_row_stride * esz) % 16 == 0 && x_row_stride % 4 == 0 && dx_row_stride % 4 == 0 &&
+              dxs_row_stride % 4 == 0 && (long long)rows * groups >= 4 * kRingRows * fc_num_sms(device);
+    for (int g = 0; ok && g < groups; ++g)
+      ok = ((reinterpret_cast<uintptr_t>(dy[g]) | reinterpret_cast<uintptr_t>(x[g]) | reinterpret_cast<uintptr_t>(dx[g]) |
+             reinterpret_cast<uintptr_t>(at(dxs_bf16, g))) & 15) == 0;
+    if (ok) {
+      const int row_bytes = d * esz + d * 4 + (accumulate ? d * 4 : 0);
+      const int stage_bytes = kRingRows * row_bytes;
+      // two CTAs per SM (16 consumer warps hide the shuffle / shared-memory latencies of the per-row reductions) when
+      // d <= 384 leaves room for >= 3 stages each; otherwise one CTA with the whole budget
+      const int ctas_per_sm = (d <= 384 && (100 * 1024) / stage_bytes >= 3) ? 2 : 1;
+      int stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / stage_bytes;
+      if (stages > 8) stages = 8;
+      const int part_bytes = 3 * kRingRows * d * 4;
+      if (stages >= 2 && stages * stage_bytes >= part_bytes) {
+        const int smem_ring = stages * stage_bytes + 2 * stages * 8 + 64;
+        const int n_chunks = (rows + kRingRows - 1) / kRingRows;
+        int gx = (fc_num_sms(device) * ctas_per_sm + groups - 1) / groups;   // resident CTAs over all groups
+        if (gx < 1) gx = 1;
+        if (gx > n_chunks) gx = n_chunks;
+        const int rpg_ = rows_per_group > 0 ? rows_per_group : 1;
+#define FC_LN_RING(NV)                                                                                             \
+  do {                                                                                                             \
+    if (dy_is_bf16) {                                                                                              \
+      FC_SMEM_OPT_IN((ln_bwd_ring_kernel<NV, true>), 220 * 1024);                                                  \
+      ln_bwd_ring_kernel<NV, true><<<dim3(gx, groups), kRingThreads, smem_ring, st0>>>(                            \
+          S, dy_row_stride, x_row_stride, dx_row_stride, accumulate, dxs_row_stride, rpg_, rows, d, stages);       \
+    } else {                                                                                                       \
+      FC_SMEM_OPT_IN((ln_bwd_ring_kernel<NV, false>), 220 * 1024);                                                 \
+      ln_bwd_ring_kernel<NV, false><<<dim3(gx, groups), kRingThreads, smem_ring, st0>>>(                           \
+          S, dy_row_stride, x_row_stride, dx_row_stride, accumulate, dxs_row_stride, rpg_, rows, d, stages);       \
+    }                                                                                                              \
+  } while (0)
+        const int nv_ = (d + 127) / 128;
+        if (nv_ <= 1) FC_LN_RING(1); else if (nv_ == 2) FC_LN_RING(2); else if (nv_ == 3) FC_LN_RING(3);
+        else if (nv_ == 4) FC_LN_RING(4); else if (nv_ <= 6) FC_LN_RING(6); else FC_LN_RING(8);
+#undef FC_LN_RING
+        FC_LAUNCH_CHECK();
+        return FC_OK;
+      }
+    }
   }
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;

@@ -112,3 +112,37 @@ def test_layernorm_forward_backward(rows, d, eps, cuda):
     xr2 = x.clone().requires_grad_(True)
     F.layer_norm(xr2, (d,), g, b, eps).backward(dy.to(torch.bfloat16).float())
     _close(dx2, xr2.grad, 1e-4, 1e-4, "ln bwd bf16 dy")
+
+
+@pytest.mark.parametrize("rows,d,accumulate,bf16_dy", [(22064, 384, True, True), (7168, 384, True, True), (6000, 768, True, True),
+                                                       (5003, 384, False, False), (18912, 768, True, True)])
+def test_layernorm_backward_streamed_large(rows, d, accumulate, bf16_dy, cuda):
+    """Launches big enough for the bulk-copy ring version of the LayerNorm backward (>= 4 736 rows): the bench's own
+    shapes (112 x 197 / 112 x 64 rows at d=384, 96 x 197 at d=768), ragged row counts, with and without the running-dx
+    accumulation, against torch's autograd."""
+    torch.manual_seed(3)
+    x = torch.randn(rows, d, device=cuda) * 2 + 0.5
+    g = torch.randn(d, device=cuda) * 0.2 + 1
+    b = torch.randn(d, device=cuda) * 0.1
+    _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5, bf16_out=True)
+    dy = torch.randn(rows, d, device=cuda)
+    if bf16_dy:
+        dy = dy.to(torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.float())
+    dx0 = torch.randn(rows, d, device=cuda)
+    dx = dx0.clone()
+    group = 197
+    scale = torch.rand((rows + group - 1) // group, device=cuda) + 0.5
+    dxs = torch.empty(rows, d, dtype=torch.bfloat16, device=cuda)
+    dgamma, dbeta = torch.zeros(d, device=cuda), torch.zeros(d, device=cuda)
+    colsum = torch.zeros(d, device=cuda)
+    ops.layernorm_bwd(dy, x, mean, rstd, g, dx, accumulate, dxs=dxs, row_scale=scale, rows_per_group=group, dgamma=dgamma,
+                      dbeta=dbeta, dxs_colsum=colsum)
+    want = (dx0 + xr.grad) if accumulate else xr.grad
+    _close(dx, want, 1e-4, 1e-4, "dx")
+    _close(dxs, want * scale.repeat_interleave(group)[:rows, None], 2 ** -8, 1e-3, "dxs")
+    _close(colsum, dxs.float().sum(0), 1e-4, 2e-3 * rows ** 0.5, "colsum of dxs")
+    _close(dgamma, gr.grad, 1e-3, 2e-3 * rows ** 0.5, "dgamma")
+    _close(dbeta, br.grad, 1e-3, 2e-3 * rows ** 0.5, "dbeta")
