@@ -75,7 +75,7 @@ struct GroupPtrs {
   float* colsum;            // EPI_MULAUX: += column sums of the output (bias gradient), or null
   const float* pos;         // EPI_PATCH: pos_embed [(P+1), N]
 };
-struct GroupMaps { CUtensorMap a, b, o, o2, r; };
+struct GroupMaps { CUtensorMap a, b, o, o2, r, a_lo, b_lo; };   // a_lo / b_lo: split-operand (fp32-accurate) mode
 struct AllMaps { GroupMaps g[FC_GEMM_MAX_GROUPS]; };
 
 struct GemmParams {
@@ -90,6 +90,7 @@ struct GemmParams {
   float alpha;
   int debug;                // measurement aid (FC_GEMM_DEBUG env): 1 = skip epilogue work, 2 = skip TMA+MMA work
   int pair;                 // 1: CTA pairs (cta_group::2) compute 256 x BN tiles, each CTA stages its 128 rows of A and half of B
+  int split;                // 1: split operands A = A_hi + A_lo, B = B_hi + B_lo (bf16 pairs): acc = A_hi B_hi + A_hi B_lo + A_lo B_hi
   GroupPtrs g[FC_GEMM_MAX_GROUPS];
 };
 
@@ -482,6 +483,10 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
     if (EPI != FC_EPI_PATCH) prefetch_tmap(&gm.o);
     if (EPI == FC_EPI_GELU) prefetch_tmap(&gm.o2);
     if (EpiTraits<EPI>::kLoads) prefetch_tmap(&gm.r);
+    if (p.split) {
+      prefetch_tmap(&gm.a_lo);
+      prefetch_tmap(&gm.b_lo);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -517,10 +522,12 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
       for (int tile = walk.first; tile < walk.total; tile += walk.step) {
         int grp, split, m_blk, n_blk;
         walk.decode(tile, grp, split, m_blk, n_blk);
-        const CUtensorMap* tmA = &maps.g[grp].a;
-        const CUtensorMap* tmB = &maps.g[grp].b;
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        // split-operand mode: three passes over the K range — (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi) — into one accumulator
+        for (int pass = 0; pass < (p.split ? 3 : 1); ++pass) {
+        const CUtensorMap* tmA = pass == 2 ? &maps.g[grp].a_lo : &maps.g[grp].a;
+        const CUtensorMap* tmB = pass == 1 ? &maps.g[grp].b_lo : &maps.g[grp].b;
         for (int kb = (p.debug & 2) ? kb1 : kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * stage_bytes;
@@ -562,6 +569,7 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -581,7 +589,8 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
           mbar_arrive(&tmem_full_bar[buf]);
           continue;
         }
-        for (int kb = kb0; kb < kb1; ++kb) {
+        uint32_t acc_flag = 0;                 // 0 for the very first MMA of the tile, 1 afterwards
+        for (int vkb = 0, nvkb = (kb1 - kb0) * (p.split ? 3 : 1); vkb < nvkb; ++vkb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -594,8 +603,9 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
                                      : umma_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            if constexpr (pair) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (pair) umma_bf16_pair(d_tmem, ad, bd, idesc, acc_flag);
+            else umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+            acc_flag = 1u;
           }
           if constexpr (pair) umma_commit_pair(&empty_bar[s]);   // slot free in both CTAs once these MMAs retire
           else umma_commit(&empty_bar[s]);     // smem slot free once these MMAs retire
@@ -882,17 +892,19 @@ extern "C" long long fc_gemm_profile_collect(double* total_ms, double* total_flo
   return (long long)g_prof.size();
 }
 
-extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void* const* A, long long lda, int a_mn_major,
-                                    const void* const* B, long long ldb, int b_mn_major, int epi, void* const* out,
-                                    void* const* out2, long long ldo, const float* const* bias,
-                                    const float* const* resid, const float* const* row_scale, int rows_per_group,
-                                    const void* const* aux, const float* const* pos, int patches, float alpha,
-                                    int splits, float* const* colsum, int device, void* stream) {
+namespace {
+int gemm_grouped_impl(int groups, int M, int N, int K, const void* const* A, const void* const* A_lo, long long lda,
+                      int a_mn_major, const void* const* B, const void* const* B_lo, long long ldb, int b_mn_major, int epi,
+                      void* const* out, void* const* out2, long long ldo, const float* const* bias,
+                      const float* const* resid, const float* const* row_scale, int rows_per_group,
+                      const void* const* aux, const float* const* pos, int patches, float alpha, int splits,
+                      float* const* colsum, int device, void* stream) {
   FC_REQUIRE(groups >= 1 && groups <= FC_GEMM_MAX_GROUPS, "fc_gemm_bf16: %d groups (1..%d)", groups, FC_GEMM_MAX_GROUPS);
   FC_REQUIRE(M > 0 && N > 0 && K > 0, "fc_gemm_bf16: empty problem %d %d %d", M, N, K);
   FC_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 4 == 0, "fc_gemm_bf16: N, lda, ldb must be multiples of 8");
   FC_REQUIRE(epi >= FC_EPI_BF16 && epi <= FC_EPI_PATCH, "fc_gemm_bf16: bad epilogue %d", epi);
   FC_REQUIRE(A != nullptr && B != nullptr && out != nullptr, "fc_gemm_bf16: null operand table");
+  FC_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "fc_gemm_bf16: split operands need both low-order tables");
   auto at = [](auto tbl, int g) { return tbl ? tbl[g] : nullptr; };
   for (int g = 0; g < groups; ++g) {
     FC_REQUIRE(A[g] != nullptr && B[g] != nullptr && out[g] != nullptr, "fc_gemm_bf16: null operand / output (group %d)", g);
@@ -958,7 +970,8 @@ extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void*
       bn = force_bn;
       p.n_tiles = (N + bn - 1) / bn;
     }
-    p.pair = (use_pairs && epi != FC_EPI_PATCH && (!b_mn_major || bn % 128 == 0) && !(p.debug & 2)) ? 1 : 0;
+    p.split = A_lo != nullptr ? 1 : 0;
+    p.pair = (use_pairs && !p.split && epi != FC_EPI_PATCH && (!b_mn_major || bn % 128 == 0) && !(p.debug & 2)) ? 1 : 0;
   }
   AllMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -971,6 +984,13 @@ extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void*
     if (rc) return rc;
     rc = b_mn_major ? make_tmap(&gm.b, B[g], K, N, ldb, 64, 64) : make_tmap(&gm.b, B[g], N, K, ldb, 64, p.pair ? bn / 2 : bn);
     if (rc) return rc;
+    if (p.split) {
+      FC_REQUIRE(A_lo[g] != nullptr && B_lo[g] != nullptr, "fc_gemm_bf16: null low-order operand (group %d)", g);
+      rc = a_mn_major ? make_tmap(&gm.a_lo, A_lo[g], K, M, lda, 64, 64) : make_tmap(&gm.a_lo, A_lo[g], M, K, lda, 64, BM);
+      if (rc) return rc;
+      rc = b_mn_major ? make_tmap(&gm.b_lo, B_lo[g], K, N, ldb, 64, 64) : make_tmap(&gm.b_lo, B_lo[g], N, K, ldb, 64, bn);
+      if (rc) return rc;
+    }
     // epilogue tiles: 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), stored / reduced / loaded by TMA
     if (epi != FC_EPI_PATCH) {
       FC_REQUIRE((reinterpret_cast<uintptr_t>(out[g]) & 15) == 0 && (ldo * (out16 ? 2 : 4)) % 16 == 0,
@@ -1001,6 +1021,37 @@ extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void*
   if (bn == 256) return launch_bn<256, 0>(maps, p, am, bm, device, st);
   if (bn == 192) return launch_bn<192, 0>(maps, p, am, bm, device, st);
   return launch_bn<128, 0>(maps, p, am, bm, device, st);
+}
+}  // namespace
+
+extern "C" int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void* const* A, long long lda, int a_mn_major,
+                                    const void* const* B, long long ldb, int b_mn_major, int epi, void* const* out,
+                                    void* const* out2, long long ldo, const float* const* bias,
+                                    const float* const* resid, const float* const* row_scale, int rows_per_group,
+                                    const void* const* aux, const float* const* pos, int patches, float alpha,
+                                    int splits, float* const* colsum, int device, void* stream) {
+  return gemm_grouped_impl(groups, M, N, K, A, nullptr, lda, a_mn_major, B, nullptr, ldb, b_mn_major, epi, out, out2, ldo, bias,
+                           resid, row_scale, rows_per_group, aux, pos, patches, alpha, splits, colsum, device, stream);
+}
+
+// fp32-accurate GEMM on the bf16 tensor pipe: each operand is a (hi, lo) pair of bf16 matrices, X = X_hi + X_lo with
+// X_lo = bf16(X - X_hi) (16 mantissa bits), and the accumulator receives A_hi B_hi + A_hi B_lo + A_lo B_hi — relative
+// error ~2^-16 per product, against 2^-8 for plain bf16 operands and 2^-10 for tcgen05's kind::tf32.  Used by the
+// validation mode (precision = 'fp32'); only the fp32-output epilogues make sense with it.
+extern "C" int fc_gemm_split(int M, int N, int K, const void* A_hi, const void* A_lo, long long lda, int a_mn_major,
+                             const void* B_hi, const void* B_lo, long long ldb, int b_mn_major, int epi, void* out,
+                             long long ldo, const float* bias, const float* resid, const float* row_scale,
+                             int rows_per_group, const float* pos, int patches, float alpha, int splits, int device,
+                             void* stream) {
+  FC_REQUIRE(epi == FC_EPI_F32 || epi == FC_EPI_RESID || epi == FC_EPI_ATOMIC_F32 || epi == FC_EPI_PATCH,
+             "fc_gemm_split: only the fp32-output epilogues (F32, RESID, ATOMIC_F32, PATCH)");
+  FC_REQUIRE(A_hi && A_lo && B_hi && B_lo && out, "fc_gemm_split: null operand");
+  void* out2 = nullptr;
+  const void* aux = nullptr;
+  float* colsum = nullptr;
+  return gemm_grouped_impl(1, M, N, K, &A_hi, &A_lo, lda, a_mn_major, &B_hi, &B_lo, ldb, b_mn_major, epi, &out, &out2, ldo,
+                           &bias, &resid, &row_scale, rows_per_group, &aux, &pos, patches, alpha, splits, &colsum, device,
+                           stream);
 }
 
 // One operand set: the plain GEMM (ref: every F.linear of the reference's Block).

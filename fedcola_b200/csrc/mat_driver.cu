@@ -297,6 +297,294 @@ int check_desc(const fc_mat_desc* m, int B) {
   return FC_OK;
 }
 
+bool is_retrieval(const fc_mat_desc* m, int e, int feat_out);
+
+// =====================================================================================================
+// fp32-accurate validation mode (m->precise): the same network with fp32 activations, split-operand GEMMs
+// (fc_gemm_split: 3 tcgen05 passes over (hi, lo) bf16 pairs), fp32 FMA attention, exact erff GELU.  One client at a
+// time, nothing fused, nothing tuned: it exists to hold the fast path to the reference's fp32 arithmetic at 1e-4.
+// =====================================================================================================
+struct PEnc {
+  float* x_in[FC_MAX_DEPTH + 1];
+  float *x_mid[FC_MAX_DEPTH], *ln1[FC_MAX_DEPTH], *ln2[FC_MAX_DEPTH], *qkv[FC_MAX_DEPTH], *ao[FC_MAX_DEPTH],
+      *pre[FC_MAX_DEPTH], *act[FC_MAX_DEPTH];
+  float *mean1[FC_MAX_DEPTH], *rstd1[FC_MAX_DEPTH], *mean2[FC_MAX_DEPTH], *rstd2[FC_MAX_DEPTH], *lse[FC_MAX_DEPTH];
+  float *patches, *mean_e, *rstd_e, *mean_f, *rstd_f, *feat, *featn, *fnorm, *logits;
+  float *dx, *d_act, *d_pre, *d_ln, *d_ao, *d_qkv, *dxp, *dfeat;
+  __nv_bfloat16* dxp_scratch;
+};
+struct PWs {
+  PEnc enc[2];
+  __nv_bfloat16 *sa_hi, *sa_lo, *sb_hi, *sb_lo;      // split scratch of the two GEMM operands
+  float *sim, *lse_ws, *da, *db, *dlogits, *scalars, *seg_sumsq;
+  size_t bytes;
+};
+
+void carve_precise(const fc_mat_desc* m, int B, void* base, PWs* w) {
+  Carver c{reinterpret_cast<uint8_t*>(base)};
+  const int d = m->d, hid = m->hidden, L = m->depth, H = m->heads;
+  int maxC = 1;
+  size_t max_op = 0;
+  for (int e = 0; e < 2; ++e) {
+    if (!m->has_enc[e]) continue;
+    PEnc& s = w->enc[e];
+    const size_t N = tokens_of(m, e), T = (size_t)B * N;
+    const size_t widest = (size_t)(hid > 3 * d ? hid : 3 * d);
+    if (T * (widest > 768 ? widest : 768) > max_op) max_op = T * (widest > 768 ? widest : 768);
+    for (int j = 0; j <= L; ++j) s.x_in[j] = c.take<float>(T * d);
+    for (int j = 0; j < L; ++j) {
+      s.x_mid[j] = c.take<float>(T * d);
+      s.ln1[j] = c.take<float>(T * d);
+      s.ln2[j] = c.take<float>(T * d);
+      s.qkv[j] = c.take<float>(T * 3 * d);
+      s.ao[j] = c.take<float>(T * d);
+      s.pre[j] = c.take<float>(T * hid);
+      s.act[j] = c.take<float>(T * hid);
+      s.mean1[j] = c.take<float>(T);
+      s.rstd1[j] = c.take<float>(T);
+      s.mean2[j] = c.take<float>(T);
+      s.rstd2[j] = c.take<float>(T);
+      s.lse[j] = c.take<float>((size_t)B * H * N);
+    }
+    s.patches = e == 0 ? c.take<float>((size_t)B * m->patches * 768) : nullptr;
+    s.mean_e = c.take<float>(T);
+    s.rstd_e = c.take<float>(T);
+    s.mean_f = c.take<float>(B);
+    s.rstd_f = c.take<float>(B);
+    s.feat = c.take<float>((size_t)B * d);
+    s.featn = c.take<float>((size_t)B * d);
+    s.fnorm = c.take<float>(B);
+    const int C = m->num_classes[e] > 0 ? m->num_classes[e] : 1;
+    if (C > maxC) maxC = C;
+    s.logits = c.take<float>((size_t)B * C);
+    s.dx = c.take<float>(T * d);
+    s.d_act = c.take<float>(T * hid);
+    s.d_pre = c.take<float>(T * hid);
+    s.d_ln = c.take<float>(T * d);
+    s.d_ao = c.take<float>(T * d);
+    s.d_qkv = c.take<float>(T * 3 * d);
+    s.dxp = e == 0 ? c.take<float>((size_t)B * m->patches * d) : nullptr;
+    s.dxp_scratch = e == 0 ? c.take<__nv_bfloat16>((size_t)B * m->patches * d) : nullptr;
+    s.dfeat = c.take<float>((size_t)B * d);
+  }
+  w->sa_hi = c.take<__nv_bfloat16>(max_op);
+  w->sa_lo = c.take<__nv_bfloat16>(max_op);
+  w->sb_hi = c.take<__nv_bfloat16>(max_op);
+  w->sb_lo = c.take<__nv_bfloat16>(max_op);
+  w->sim = c.take<float>((size_t)B * B);
+  w->lse_ws = c.take<float>(2 * (size_t)B);
+  w->da = c.take<float>((size_t)B * d);
+  w->db = c.take<float>((size_t)B * d);
+  w->dlogits = c.take<float>((size_t)B * maxC);
+  w->scalars = c.take<float>(8);
+  w->seg_sumsq = c.take<float>(FC_MAX_SEGMENTS);
+  w->bytes = c.off;
+}
+
+struct PCtx {
+  const fc_mat_desc* m;
+  const float* params;
+  float* grads;
+  const __nv_bfloat16* ops;      // W_eff hi parts; lo parts at ops + m->op_lo_offset
+  int B, device;
+  void* stream;
+  const float* droppath;
+  PWs w;
+  const float* p(long long off) const { return off >= 0 ? params + off : nullptr; }
+  float* g(long long off) const { return (off >= 0 && grads) ? grads + off : nullptr; }
+  const float* dp(int e, int j, int which) const {
+    return droppath ? droppath + (((size_t)e * m->depth + j) * 2 + which) * B : nullptr;
+  }
+};
+
+// out[M, N] = epi( X[M, K] W[N, K]^T )            (forward Linear; W by operand offset)
+int plinear(PCtx& c, int M, int N, int K, const float* X, long long w_off, int epi, float* out, const float* bias,
+            const float* resid, const float* row_scale, int rpg, const float* pos = nullptr, int patches = 0) {
+  TRY(fc_split_bf16(X, c.w.sa_hi, c.w.sa_lo, (long long)M * K, K, nullptr, 0, c.device, c.stream));
+  return fc_gemm_split(M, N, K, c.w.sa_hi, c.w.sa_lo, K, 0, c.ops + w_off, c.ops + c.m->op_lo_offset + w_off, K, 0, epi, out, N,
+                       bias, resid, row_scale, rpg, pos, patches, 1.0f, 1, c.device, c.stream);
+}
+// dX[M, K] = dY[M, N] W[N, K]     (dY optionally scaled per row group: the DropPath factor of the branch)
+int pdx(PCtx& c, int M, int N, int K, const float* dY, const float* row_scale, int rpg, long long w_off, float* dX) {
+  TRY(fc_split_bf16(dY, c.w.sa_hi, c.w.sa_lo, (long long)M * N, N, row_scale, rpg, c.device, c.stream));
+  return fc_gemm_split(M, K, N, c.w.sa_hi, c.w.sa_lo, N, 0, c.ops + w_off, c.ops + c.m->op_lo_offset + w_off, K, 1, FC_EPI_F32, dX,
+                       K, nullptr, nullptr, nullptr, 0, nullptr, 0, 1.0f, 1, c.device, c.stream);
+}
+// dW[N, K] += dY[M, N]^T X[M, K]  (sa must already hold the split of (scaled) dY: call right after pdx); db += colsum(dY)
+int pdw(PCtx& c, int M, int N, int K, const float* X, float* dW) {
+  TRY(fc_split_bf16(X, c.w.sb_hi, c.w.sb_lo, (long long)M * K, K, nullptr, 0, c.device, c.stream));
+  return fc_gemm_split(N, K, M, c.w.sa_hi, c.w.sa_lo, N, 1, c.w.sb_hi, c.w.sb_lo, K, 1, FC_EPI_ATOMIC_F32, dW, K, nullptr, nullptr,
+                       nullptr, 0, nullptr, 0, 1.0f, 0, c.device, c.stream);
+}
+
+int p_encoder_forward(PCtx& c, int e, const float* img, const long long* ids) {
+  const fc_mat_desc* m = c.m;
+  PEnc& s = c.w.enc[e];
+  const int d = m->d, hid = m->hidden, L = m->depth, H = m->heads, B = c.B;
+  const int N = tokens_of(m, e), T = B * N;
+  if (e == 0) {
+    FC_REQUIRE(img != nullptr, "fc_mat_forward: image input missing");
+    TRY(fc_im2col16_f32(img, s.patches, B, m->in_chans, m->img_size, c.device, c.stream));
+    // cls rows: x[b, 0, :] = cls + pos[0]  (the bf16 patch matrix this call also writes goes to the dW scratch: unused)
+    TRY(fc_im2col16(img, s.dxp_scratch ? (void*)c.w.sb_hi : nullptr, s.x_in[0], c.p(m->img_cls), c.p(m->img_pos), B,
+                    m->in_chans, m->img_size, d, c.device, c.stream));
+    TRY(plinear(c, B * m->patches, d, 768, s.patches, m->op_pw, FC_EPI_PATCH, s.x_in[0], c.p(m->img_pb), nullptr, nullptr, 0,
+                c.p(m->img_pos), m->patches));
+  } else {
+    FC_REQUIRE(ids != nullptr, "fc_mat_forward: token ids missing");
+    TRY(fc_text_embed_fwd(ids, c.p(m->txt_word), c.p(m->txt_pos), c.p(m->txt_type), c.p(m->txt_lnw), c.p(m->txt_lnb),
+                          1e-12f, s.x_in[0], s.mean_e, s.rstd_e, B, N, d, c.device, c.stream));
+  }
+  for (int j = 0; j < L; ++j) {
+    const long long* o = m->blk[e][j];
+    const long long* op = m->op[e][j];
+    TRY(fc_layernorm_fwd(s.x_in[j], d, c.p(o[N1W]), c.p(o[N1B]), 1e-5f, nullptr, s.ln1[j], s.mean1[j], s.rstd1[j], T, d,
+                         c.device, c.stream));
+    TRY(plinear(c, T, 3 * d, d, s.ln1[j], op[L_QKV], FC_EPI_F32, s.qkv[j], c.p(o[QKVB]), nullptr, nullptr, 0));
+    TRY(fc_attention_f32_fwd(s.qkv[j], s.ao[j], s.lse[j], B, N, H, c.device, c.stream));
+    TRY(plinear(c, T, d, d, s.ao[j], op[L_PROJ], FC_EPI_RESID, s.x_mid[j], c.p(o[PROJB]), s.x_in[j], c.dp(e, j, 0), N));
+    TRY(fc_layernorm_fwd(s.x_mid[j], d, c.p(o[N2W]), c.p(o[N2B]), 1e-5f, nullptr, s.ln2[j], s.mean2[j], s.rstd2[j], T, d,
+                         c.device, c.stream));
+    TRY(plinear(c, T, hid, d, s.ln2[j], op[L_FC1], FC_EPI_F32, s.pre[j], c.p(o[FC1B]), nullptr, nullptr, 0));
+    TRY(fc_gelu_f32_fwd(s.pre[j], s.act[j], (long long)T * hid, c.device, c.stream));
+    TRY(plinear(c, T, d, hid, s.act[j], op[L_FC2], FC_EPI_RESID, s.x_in[j + 1], c.p(o[FC2B]), s.x_mid[j], c.dp(e, j, 1), N));
+  }
+  TRY(fc_layernorm_fwd(s.x_in[L], (long long)N * d, c.p(m->norm_w), c.p(m->norm_b), 1e-6f, nullptr, s.feat, s.mean_f,
+                       s.rstd_f, B, d, c.device, c.stream));
+  return FC_OK;
+}
+
+int p_encoder_backward(PCtx& c, int e, const long long* ids) {
+  const fc_mat_desc* m = c.m;
+  PEnc& s = c.w.enc[e];
+  const int d = m->d, hid = m->hidden, L = m->depth, H = m->heads, B = c.B;
+  const int N = tokens_of(m, e), T = B * N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(c.stream);
+  FC_CUDA_CHECK(cudaMemsetAsync(s.dx, 0, sizeof(float) * (size_t)T * d, st));
+  TRY(fc_layernorm_bwd(s.dfeat, 0, d, s.x_in[L], (long long)N * d, s.mean_f, s.rstd_f, c.p(m->norm_w), s.dx,
+                       (long long)N * d, 0, nullptr, 0, nullptr, 1, c.g(m->norm_w), c.g(m->norm_b), nullptr, B, d, c.device,
+                       c.stream));
+  for (int j = L - 1; j >= 0; --j) {
+    const long long* o = m->blk[e][j];
+    const long long* op = m->op[e][j];
+    // ---- mlp branch: the branch gradient is dp2 * dx (per-sample DropPath factor)
+    const float* dp2 = c.dp(e, j, 1);
+    TRY(fc_colsum_f32(s.dx, d, T, d, dp2, N, c.g(o[FC2B]), c.device, c.stream));
+    TRY(pdx(c, T, d, hid, s.dx, dp2, N, op[L_FC2], s.d_act));                // sa = split(dp2 * dx)
+    TRY(pdw(c, T, d, hid, s.act[j], c.g(o[FC2W])));
+    TRY(fc_gelu_f32_bwd(s.d_act, s.pre[j], s.d_pre, (long long)T * hid, c.device, c.stream));
+    TRY(fc_colsum_f32(s.d_pre, hid, T, hid, nullptr, 0, c.g(o[FC1B]), c.device, c.stream));
+    TRY(pdx(c, T, hid, d, s.d_pre, nullptr, 0, op[L_FC1], s.d_ln));
+    TRY(pdw(c, T, hid, d, s.ln2[j], c.g(o[FC1W])));
+    TRY(fc_layernorm_bwd(s.d_ln, 0, d, s.x_mid[j], d, s.mean2[j], s.rstd2[j], c.p(o[N2W]), s.dx, d, 1, nullptr, 0, nullptr, 1,
+                         c.g(o[N2W]), c.g(o[N2B]), nullptr, T, d, c.device, c.stream));
+    // ---- attention branch
+    const float* dp1 = c.dp(e, j, 0);
+    TRY(fc_colsum_f32(s.dx, d, T, d, dp1, N, c.g(o[PROJB]), c.device, c.stream));
+    TRY(pdx(c, T, d, d, s.dx, dp1, N, op[L_PROJ], s.d_ao));
+    TRY(pdw(c, T, d, d, s.ao[j], c.g(o[PROJW])));
+    FC_CUDA_CHECK(cudaMemsetAsync(s.d_qkv, 0, sizeof(float) * (size_t)T * 3 * d, st));
+    TRY(fc_attention_f32_bwd(s.qkv[j], s.ao[j], s.d_ao, s.lse[j], s.d_qkv, B, N, H, c.device, c.stream));
+    TRY(fc_colsum_f32(s.d_qkv, 3 * d, T, 3 * d, nullptr, 0, c.g(o[QKVB]), c.device, c.stream));
+    TRY(pdx(c, T, 3 * d, d, s.d_qkv, nullptr, 0, op[L_QKV], s.d_ln));
+    TRY(pdw(c, T, 3 * d, d, s.ln1[j], c.g(o[QKVW])));
+    TRY(fc_layernorm_bwd(s.d_ln, 0, d, s.x_in[j], d, s.mean1[j], s.rstd1[j], c.p(o[N1W]), s.dx, d, 1, nullptr, 0, nullptr, 1,
+                         c.g(o[N1W]), c.g(o[N1B]), nullptr, T, d, c.device, c.stream));
+  }
+  if (e == 0) {
+    TRY(fc_patch_bwd_prep(s.dx, s.dxp_scratch, c.g(m->img_pos), c.g(m->img_cls), c.g(m->img_pb), B, m->patches, d, c.device,
+                          c.stream));
+    TRY(fc_drop_cls_rows(s.dx, s.dxp, B, m->patches, d, c.device, c.stream));
+    const int M = B * m->patches;
+    TRY(fc_split_bf16(s.dxp, c.w.sa_hi, c.w.sa_lo, (long long)M * d, d, nullptr, 0, c.device, c.stream));
+    TRY(pdw(c, M, d, 768, s.patches, c.g(m->img_pw)));
+  } else {
+    TRY(fc_text_embed_bwd(s.dx, ids, c.p(m->txt_word), c.p(m->txt_pos), c.p(m->txt_type), c.p(m->txt_lnw), s.mean_e,
+                          s.rstd_e, c.g(m->txt_word), c.g(m->txt_pos), c.g(m->txt_type), c.g(m->txt_lnw), c.g(m->txt_lnb), B,
+                          N, d, c.device, c.stream));
+  }
+  return FC_OK;
+}
+
+int p_forward(const fc_mat_desc* m, const float* params, const void* operands, void* workspace, int B, const float* img,
+              const long long* ids, const float* droppath, int feat_out, float* out0, float* out1, int device, void* stream) {
+  PCtx c{m, params, nullptr, reinterpret_cast<const __nv_bfloat16*>(operands), B, device, stream, droppath, {}};
+  carve_precise(m, B, workspace, &c.w);
+  float* outs[2] = {out0, out1};
+  for (int e = 0; e < 2; ++e) {
+    if (!m->has_enc[e]) continue;
+    TRY(p_encoder_forward(c, e, img, ids));
+    PEnc& s = c.w.enc[e];
+    if (is_retrieval(m, e, feat_out)) {
+      TRY(fc_l2norm_fwd(s.feat, s.featn, s.fnorm, B, m->d, device, stream));
+      if (outs[e])
+        FC_CUDA_CHECK(cudaMemcpyAsync(outs[e], s.featn, sizeof(float) * (size_t)B * m->d, cudaMemcpyDeviceToDevice,
+                                      reinterpret_cast<cudaStream_t>(stream)));
+    } else {
+      TRY(fc_head_fwd(s.feat, c.p(m->head_w[e]), c.p(m->head_b[e]), s.logits, B, m->d, m->num_classes[e], device, stream));
+      if (outs[e])
+        FC_CUDA_CHECK(cudaMemcpyAsync(outs[e], s.logits, sizeof(float) * (size_t)B * m->num_classes[e],
+                                      cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    }
+  }
+  return FC_OK;
+}
+
+int p_backward(const fc_mat_desc* m, const float* params, const void* operands, void* workspace, int B,
+               const long long* ids, const float* droppath, int feat_out, const float* dout0, const float* dout1, float* grads,
+               const void* aux_layers, int n_aux_layers, int n_aux_chunks, int device, void* stream) {
+  PCtx c{m, params, grads, reinterpret_cast<const __nv_bfloat16*>(operands), B, device, stream, droppath, {}};
+  carve_precise(m, B, workspace, &c.w);
+  const float* douts[2] = {dout0, dout1};
+  for (int e = 0; e < 2; ++e) {
+    if (!m->has_enc[e] || douts[e] == nullptr) continue;
+    PEnc& s = c.w.enc[e];
+    if (is_retrieval(m, e, feat_out)) {
+      TRY(fc_l2norm_bwd(douts[e], s.featn, s.fnorm, s.dfeat, B, m->d, device, stream));
+    } else {
+      TRY(fc_head_bwd(douts[e], s.feat, c.p(m->head_w[e]), c.g(m->head_w[e]), c.g(m->head_b[e]), s.dfeat, B, m->d,
+                      m->num_classes[e], device, stream));
+    }
+    TRY(p_encoder_backward(c, e, ids));
+  }
+  if (n_aux_layers > 0)
+    TRY(fc_aux_grads(params, grads, aux_layers, n_aux_layers, n_aux_chunks, m->aux_trained, device, stream));
+  return FC_OK;
+}
+
+// forward + loss + backward of one client in the validation mode (the optimizer part is shared with the fast path)
+int p_step_fwd_bwd(const fc_mat_desc* m, const fc_step_args* a, int device, void* stream) {
+  const int B = a->B, d = m->d;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PCtx c{m, a->params, a->grads, reinterpret_cast<const __nv_bfloat16*>(a->operands), B, device, stream, a->droppath, {}};
+  carve_precise(m, B, a->workspace, &c.w);
+  for (int e = 0; e < 2; ++e)
+    if (m->has_enc[e]) TRY(p_encoder_forward(c, e, a->img, a->ids));
+  FC_CUDA_CHECK(cudaMemsetAsync(a->grads, 0, sizeof(float) * (size_t)a->arena_floats, st));
+  PWs& w = c.w;
+  if (a->loss_kind == FC_LOSS_CONTRASTIVE) {
+    FC_REQUIRE(m->has_enc[0] && m->has_enc[1], "contrastive loss needs both encoders");
+    for (int e = 0; e < 2; ++e) TRY(fc_l2norm_fwd(w.enc[e].feat, w.enc[e].featn, w.enc[e].fnorm, B, d, device, stream));
+    TRY(fc_contrastive_loss(w.enc[0].featn, w.enc[1].featn, w.sim, w.lse_ws, w.da, w.db, a->stats, a->stats + 2, B, d,
+                            1.0f / 0.07f, 1.0f, device, stream));
+    TRY(fc_l2norm_bwd(w.da, w.enc[0].featn, w.enc[0].fnorm, w.enc[0].dfeat, B, d, device, stream));
+    TRY(fc_l2norm_bwd(w.db, w.enc[1].featn, w.enc[1].fnorm, w.enc[1].dfeat, B, d, device, stream));
+    TRY(p_encoder_backward(c, 0, a->ids));
+    TRY(p_encoder_backward(c, 1, a->ids));
+  } else {
+    const int e = a->loss_kind == FC_LOSS_CE_IMG ? 0 : 1;
+    const int C = m->num_classes[e];
+    FC_REQUIRE(m->has_enc[e] && C > 0 && a->labels != nullptr, "CE loss needs a classification head and labels");
+    PEnc& s = w.enc[e];
+    TRY(fc_head_fwd(s.feat, c.p(m->head_w[e]), c.p(m->head_b[e]), s.logits, B, d, C, device, stream));
+    TRY(fc_ce_loss(s.logits, a->labels, w.dlogits, a->stats, a->stats + 1, a->stats + 2, B, C, 1.0f, device, stream));
+    TRY(fc_head_bwd(w.dlogits, s.feat, c.p(m->head_w[e]), c.g(m->head_w[e]), c.g(m->head_b[e]), s.dfeat, B, d, C, device,
+                    stream));
+    TRY(p_encoder_backward(c, e, a->ids));
+  }
+  return FC_OK;
+}
+
 void init_ctx(Ctx& c, const fc_mat_desc* m, int G, int B, int device, void* stream) {
   c.m = m; c.G = G; c.B = B; c.device = device; c.stream = stream;
   for (int g = 0; g < MAXG; ++g) { c.params[g] = nullptr; c.grads[g] = nullptr; c.ops[g] = nullptr; c.droppath[g] = nullptr; }
@@ -306,6 +594,11 @@ void init_ctx(Ctx& c, const fc_mat_desc* m, int G, int B, int device, void* stre
 
 extern "C" long long fc_mat_workspace_bytes(const fc_mat_desc* m, int B) {
   if (check_desc(m, B) != FC_OK) return -1;
+  if (m->precise) {
+    PWs pw;
+    carve_precise(m, B, nullptr, &pw);
+    return (long long)pw.bytes;
+  }
   Ws w;
   carve(m, B, nullptr, &w);
   return (long long)w.bytes;
@@ -316,6 +609,8 @@ extern "C" int fc_mat_forward(const fc_mat_desc* m, const float* params, const v
                               float* out0, float* out1, int device, void* stream) {
   TRY(check_desc(m, B));
   FcDeviceGuard guard(device);
+  if (m->precise)
+    return p_forward(m, params, operands, workspace, B, img, ids, droppath, feat_out, out0, out1, device, stream);
   Ctx c;
   init_ctx(c, m, 1, B, device, stream);
   carve(m, B, workspace, &c.w[0]);
@@ -347,6 +642,9 @@ extern "C" int fc_mat_backward(const fc_mat_desc* m, const float* params, const 
                                int n_aux_chunks, int device, void* stream) {
   TRY(check_desc(m, B));
   FcDeviceGuard guard(device);
+  if (m->precise)
+    return p_backward(m, params, operands, workspace, B, ids, droppath, feat_out, dout0, dout1, grads, aux_layers,
+                      n_aux_layers, n_aux_chunks, device, stream);
   Ctx c;
   init_ctx(c, m, 1, B, device, stream);
   carve(m, B, workspace, &c.w[0]);
@@ -386,18 +684,30 @@ extern "C" int fc_client_step_group(const fc_mat_desc* m, int n, const fc_step_a
   init_ctx(c, m, n, B, device, stream);
   const float* img[MAXG] = {nullptr};
   const long long* ids[MAXG] = {nullptr};
+  float* seg_sumsq[MAXG] = {nullptr};
+  float* scalars[MAXG] = {nullptr};
   for (int g = 0; g < n; ++g) {
     const fc_step_args* a = args[g];
     FC_REQUIRE(a != nullptr && a->B == B && a->loss_kind == loss_kind, "fc_client_step_group: clients of a group must share "
                "the batch size and the loss kind");
     FC_REQUIRE((a->droppath == nullptr) == (args[0]->droppath == nullptr), "fc_client_step_group: DropPath in all or none");
     FC_REQUIRE(a->n_segments <= FC_MAX_SEGMENTS, "too many parameter segments (%d)", a->n_segments);
-    carve(m, B, a->workspace, &c.w[g]);
+    if (m->precise) {
+      PWs pw;
+      carve_precise(m, B, a->workspace, &pw);
+      seg_sumsq[g] = pw.seg_sumsq; scalars[g] = pw.scalars;
+    } else {
+      carve(m, B, a->workspace, &c.w[g]);
+      seg_sumsq[g] = c.w[g].seg_sumsq; scalars[g] = c.w[g].scalars;
+    }
     c.params[g] = a->params; c.grads[g] = a->grads; c.ops[g] = reinterpret_cast<const __nv_bfloat16*>(a->operands);
     c.droppath[g] = a->droppath;
     img[g] = a->img; ids[g] = a->ids;
   }
 
+  if (m->precise) {        // validation mode: one client at a time, fp32 activations, split-operand GEMMs
+    EACH(g) TRY(p_step_fwd_bwd(m, args[g], device, stream));
+  } else {
   // ---- forward
   for (int e = 0; e < 2; ++e)
     if (m->has_enc[e]) TRY(encoder_forward(c, e, img, ids));
@@ -432,10 +742,11 @@ extern "C" int fc_client_step_group(const fc_mat_desc* m, int n, const fc_step_a
     }
     TRY(encoder_backward(c, e, ids));
   }
+  }
   // ---- per client: aux gradients, FedProx term, clipping, optimizer step, operand refresh
   EACH(g) {
     const fc_step_args* a = args[g];
-    Ws& w = c.w[g];
+    struct { float* seg_sumsq; float* scalars; } w{seg_sumsq[g], scalars[g]};
     if (a->n_aux_layers > 0)
       TRY(fc_aux_grads(a->params, a->grads, a->aux_layers, a->n_aux_layers, a->n_aux_chunks, m->aux_trained, device, stream));
     // FedProx proximal term (fedproxclient.py:64-67): per-tensor un-squared L2 norms
@@ -463,8 +774,13 @@ extern "C" int fc_client_step_group(const fc_mat_desc* m, int n, const fc_step_a
       FC_FAIL(FC_ERR_UNSUPPORTED, "unsupported optimizer id %d", a->optimizer);
     }
     // refresh the bf16 GEMM operands (W + s*A) for the next forward
-    if (a->optimizer != FC_OPT_NONE && a->n_prep_layers > 0)
-      TRY(fc_prep_weights(a->params, a->operands, a->prep_layers, a->n_prep_layers, a->n_prep_tiles, device, stream));
+    if (a->optimizer != FC_OPT_NONE && a->n_prep_layers > 0) {
+      if (m->precise)
+        TRY(fc_prep_weights_split(a->params, a->operands, reinterpret_cast<__nv_bfloat16*>(a->operands) + m->op_lo_offset,
+                                  a->prep_layers, a->n_prep_layers, device, stream));
+      else
+        TRY(fc_prep_weights(a->params, a->operands, a->prep_layers, a->n_prep_layers, a->n_prep_tiles, device, stream));
+    }
   }
   return FC_OK;
 }

@@ -140,3 +140,46 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dxs=None, row_scale=
                                      c_int(d), c_int(_dev(x)), _st(x))
     _lib.check(rc, "fc_layernorm_bwd")
     return dx
+
+
+# ---- fp32-accurate validation mode (csrc/precise.cu, fc_gemm_split) ------------------------------------
+def split_bf16(x, row_scale=None, rows_per_group=0):
+    """fp32 tensor -> (hi, lo) bf16 pair with x ~= hi + lo (16 mantissa bits)."""
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    rc = _lib.lib().fc_split_bf16(ptr(x), ptr(hi), ptr(lo), c_ll(x.numel()), c_int(x.shape[-1]), ptr(row_scale),
+                                  c_int(rows_per_group), c_int(_dev(x)), _st(x))
+    _lib.check(rc, "fc_split_bf16")
+    return hi, lo
+
+
+def gemm_split(A, B, epi, out, *, a_mn=False, b_mn=False, bias=None, resid=None, row_scale=None, rows_per_group=0,
+               alpha=1.0, splits=1):
+    """out (+)= A · Bᵀ for fp32 A, B through split bf16 operands (3 tcgen05 passes): fp32-accurate."""
+    assert A.dtype == torch.float32 and B.dtype == torch.float32
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N = B.shape[1] if b_mn else B.shape[0]
+    ah, al = split_bf16(A)
+    bh, bl = split_bf16(B)
+    rc = _lib.lib().fc_gemm_split(c_int(M), c_int(N), c_int(K), ptr(ah), ptr(al), c_ll(A.stride(0)), c_int(int(a_mn)), ptr(bh),
+                                  ptr(bl), c_ll(B.stride(0)), c_int(int(b_mn)), c_int(epi), ptr(out), c_ll(out.stride(0)),
+                                  ptr(bias), ptr(resid), ptr(row_scale), c_int(rows_per_group), ptr(None), c_int(0),
+                                  c_f(alpha), c_int(splits), c_int(_dev(A)), _st(A))
+    _lib.check(rc, "fc_gemm_split")
+    return out
+
+
+def attention_f32(qkv, B, N, H, dout=None):
+    """fp32 FMA attention of the validation mode: returns (out, lse[, dqkv])."""
+    out = torch.empty(B, N, H * 64, dtype=torch.float32, device=qkv.device)
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    L = _lib.lib()
+    _lib.check(L.fc_attention_f32_fwd(ptr(qkv), ptr(out), ptr(lse), c_int(B), c_int(N), c_int(H), c_int(_dev(qkv)), _st(qkv)),
+               "fc_attention_f32_fwd")
+    if dout is None:
+        return out, lse
+    dqkv = torch.zeros_like(qkv)
+    _lib.check(L.fc_attention_f32_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), c_int(B), c_int(N), c_int(H),
+                                      c_int(_dev(qkv)), _st(qkv)), "fc_attention_f32_bwd")
+    return out, lse, dqkv

@@ -24,6 +24,7 @@ class MatDesc(ctypes.Structure):
                 ("img_size", c_int), ("patches", c_int), ("in_chans", c_int),
                 ("seq_len", c_int), ("vocab", c_int), ("max_text_len", c_int),
                 ("num_classes", c_int * 2), ("has_enc", c_int * 2), ("with_aux", c_int), ("aux_trained", c_int),
+                ("precise", c_int), ("op_lo_offset", c_ll),
                 ("img_pos", c_ll), ("img_cls", c_ll), ("img_pw", c_ll), ("img_pb", c_ll),
                 ("txt_word", c_ll), ("txt_pos", c_ll), ("txt_type", c_ll), ("txt_lnw", c_ll), ("txt_lnb", c_ll),
                 ("norm_w", c_ll), ("norm_b", c_ll), ("head_w", c_ll * 2), ("head_b", c_ll * 2),
@@ -58,8 +59,9 @@ def _round_up(x, a):
 class ModelPlan:
     """Everything static about one MatSpec: C descriptor, operand-arena layout, prep/aux tables."""
 
-    def __init__(self, spec: MatSpec):
+    def __init__(self, spec: MatSpec, precise=False):
         _sigs()
+        self.precise = bool(precise)
         if spec.depth > MAX_DEPTH:
             raise ValueError(f"depth {spec.depth} > {MAX_DEPTH}")
         if spec.head_dim != 64:
@@ -104,6 +106,10 @@ class ModelPlan:
                         off = _round_up(off + rows * cols, 64)
         self.desc = m
         self.operand_elems = max(off, 64)
+        # fp32-accurate validation mode: the operand arena holds W_eff as (hi, lo) bf16 pairs — lo parts after the hi parts
+        m.precise = int(self.precise)
+        m.op_lo_offset = _round_up(self.operand_elems, 64) if self.precise else 0
+        self.operand_alloc = m.op_lo_offset + self.operand_elems if self.precise else self.operand_elems
         pt = np.zeros(len(prep), dtype=PREP_DT)
         tiles = 0
         for i, (w, a, s, dst, rows, cols) in enumerate(prep):
@@ -173,28 +179,28 @@ def _to_dev(np_table, device):
 _PLAN_CACHE = {}
 
 
-def plan_for(spec: MatSpec) -> ModelPlan:
+def plan_for(spec: MatSpec, precise=False) -> ModelPlan:
     """ModelPlans are static per architecture: cache them (a round creates one runtime per sampled client)."""
-    sig = (spec.embed_dim, spec.depth, spec.num_heads, spec.modalities, spec.num_classes, spec.tasks, spec.vocab_size,
+    sig = (bool(precise), spec.embed_dim, spec.depth, spec.num_heads, spec.modalities, spec.num_classes, spec.tasks, spec.vocab_size,
            spec.max_text_len, spec.img_size, spec.patch_size, spec.in_chans, spec.mlp_ratio, spec.with_aux,
            spec.aux_trained, spec.aux_attn_only, spec.aux_mlp_only, spec.share_scope, tuple(spec.keys()))
     p = _PLAN_CACHE.get(sig)
     if p is None:
-        p = _PLAN_CACHE[sig] = ModelPlan(spec)
+        p = _PLAN_CACHE[sig] = ModelPlan(spec, precise)
     return p
 
 
 class ModelRuntime:
     """Device buffers of one model instance: bf16 operand arena, workspace, grad arena, tables."""
 
-    def __init__(self, spec: MatSpec, arena: torch.Tensor):
+    def __init__(self, spec: MatSpec, arena: torch.Tensor, precise=False):
         _lib.require_cuda(arena, "model arena")
         _sigs()
-        self.plan = plan_for(spec)
+        self.plan = plan_for(spec, precise)
         self.arena = arena
         self.device = arena.device
         self.dev_index = arena.device.index if arena.device.index is not None else torch.cuda.current_device()
-        self.operands = torch.zeros(self.plan.operand_elems, dtype=torch.bfloat16, device=self.device)
+        self.operands = torch.zeros(self.plan.operand_alloc, dtype=torch.bfloat16, device=self.device)
         dev_tables = self.plan.__dict__.setdefault("_dev_tables", {})
         if str(self.device) not in dev_tables:
             dev_tables[str(self.device)] = (_to_dev(self.plan.prep_table, self.device),
@@ -219,8 +225,15 @@ class ModelRuntime:
         return self.grads
 
     def refresh_operands(self):
-        """bf16 W_eff = W + s*A for every Linear (fc_prep_weights)."""
+        """bf16 W_eff = W + s*A for every Linear (fc_prep_weights; as (hi, lo) pairs in the validation mode)."""
         p = self.plan
+        if p.precise:
+            lo = self.operands[p.desc.op_lo_offset:]
+            rc = _lib.lib().fc_prep_weights_split(_lib.ptr(self.arena), _lib.ptr(self.operands), _lib.ptr(lo),
+                                                  _lib.ptr(self.prep_dev), c_int(len(p.prep_table)), c_int(self.dev_index),
+                                                  _lib.stream_ptr(self.device))
+            _lib.check(rc, "fc_prep_weights_split")
+            return
         rc = _lib.lib().fc_prep_weights(_lib.ptr(self.arena), _lib.ptr(self.operands), _lib.ptr(self.prep_dev),
                                         c_int(len(p.prep_table)), c_int(p.n_prep_tiles), c_int(self.dev_index),
                                         _lib.stream_ptr(self.device))
@@ -273,8 +286,9 @@ def droppath_scales(spec: MatSpec, B, device, training, mode="reference"):
 
 def _runtime(model):
     rt = model._runtime
-    if rt is None or rt.arena.data_ptr() != model.arena.data_ptr():
-        rt = ModelRuntime(model.spec, model.arena)
+    precise = getattr(model, "precision", "bf16") == "fp32"
+    if rt is None or rt.arena.data_ptr() != model.arena.data_ptr() or rt.plan.precise != precise:
+        rt = ModelRuntime(model.spec, model.arena, precise)
         model._runtime = rt
     return rt
 

@@ -113,6 +113,15 @@ int fc_gemm_bf16_grouped(int groups, int M, int N, int K, const void* const* A, 
                          const float* const* pos, int patches, float alpha, int splits, float* const* colsum,
                          int device, void* stream);
 
+/* fp32-accurate GEMM on the bf16 tensor pipe (validation mode, precision = 'fp32'): operands are (hi, lo) bf16 pairs,
+ * X = X_hi + X_lo, X_lo = bf16(X - X_hi); acc = A_hi B_hi + A_hi B_lo + A_lo B_hi (relative error ~2^-16, better than
+ * kind::tf32's 2^-10).  fp32-output epilogues only (F32, RESID, ATOMIC_F32, PATCH).
+ * ref: the reference's strict-fp32 F.linear (src/models/mome.py:58-60,112-121,143-166). */
+int fc_gemm_split(int M, int N, int K, const void* A_hi, const void* A_lo, long long lda, int a_mn_major,
+                  const void* B_hi, const void* B_lo, long long ldb, int b_mn_major, int epi, void* out, long long ldo,
+                  const float* bias, const float* resid, const float* row_scale, int rows_per_group, const float* pos,
+                  int patches, float alpha, int splits, int device, void* stream);
+
 /* Per-launch GEMM timing with CUDA events on the launching stream (measurement aid; off by default). */
 void fc_gemm_profile(int enable);
 long long fc_gemm_profile_collect(double* total_ms, double* total_flops);
@@ -226,6 +235,28 @@ int fc_aux_grads(const float* params, float* grads, const void* layers, int n_la
 int fc_colsum_bf16(const void* x, long long ld, int rows, int n, float* out, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * fp32-accurate validation mode (precision = 'fp32'): fp32 activations, split-operand GEMMs (fc_gemm_split), fp32 FMA
+ * attention.  ref: the reference's strict-fp32 arithmetic, src/models/mome.py:150-168.  Simple kernels, not tuned.
+ * ------------------------------------------------------------------------------------------------ */
+/* x (fp32, n elements, rows of row_len) [* row_scale[row / rows_per_group]] -> hi = bf16(x), lo = bf16(x - hi) */
+int fc_split_bf16(const float* x, void* hi, void* lo, long long n, int row_len, const float* row_scale,
+                  int rows_per_group, int device, void* stream);
+/* W_eff = W + s*A of every Linear as (hi, lo) pairs; `layers` as for fc_prep_weights */
+int fc_prep_weights_split(const float* params, void* hi, void* lo, const void* layers, int n_layers, int device,
+                          void* stream);
+int fc_gelu_f32_fwd(const float* pre, float* act, long long n, int device, void* stream);
+int fc_gelu_f32_bwd(const float* d_act, const float* pre, float* d_pre, long long n, int device, void* stream);
+/* out[n] += column sums of x[rows, n] (optionally row-scaled) */
+int fc_colsum_f32(const float* x, long long ld, int rows, int n, const float* row_scale, int rows_per_group, float* out,
+                  int device, void* stream);
+/* qkv fp32 [B, N, 3, H, 64]; out fp32 [B, N, H*64]; lse fp32 [B, H, N]; dqkv must be zeroed by the caller */
+int fc_attention_f32_fwd(const float* qkv, float* out, float* lse, int B, int N, int H, int device, void* stream);
+int fc_attention_f32_bwd(const float* qkv, const float* out, const float* d_out, const float* lse, float* dqkv, int B,
+                         int N, int H, int device, void* stream);
+int fc_im2col16_f32(const float* img, float* patches, int B, int in_chans, int img_size, int device, void* stream);
+int fc_drop_cls_rows(const float* dx, float* dxp, int B, int patches, int d, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Native step driver                 ref: src/models/mome.py:881-922 (ModalityAgnosticTransformer.forward),
  *   src/client/fedavgclient.py:79-102 and src/client/fedproxclient.py:64-71 (one batch of the update loop)
  * ------------------------------------------------------------------------------------------------ */
@@ -240,6 +271,10 @@ typedef struct {
   int num_classes[2];                   /* per encoder slot (0 = img, 1 = txt); <= 0: retrieval / no head */
   int has_enc[2];
   int with_aux, aux_trained;
+  int precise;                          /* 1: fp32-accurate validation mode (split-operand GEMMs, fp32 activations); the
+                                           operand arena then holds W_eff hi parts followed, op_lo_offset elements later,
+                                           by the lo parts */
+  long long op_lo_offset;
   /* float offsets into the flat param arena (the grad / optimizer arenas share the layout); -1 = absent */
   long long img_pos, img_cls, img_pw, img_pb;
   long long txt_word, txt_pos, txt_type, txt_lnw, txt_lnb;
