@@ -747,6 +747,15 @@ extern "C" int fc_client_step_group(const fc_mat_desc* m, int n, const fc_step_a
   EACH(g) {
     const fc_step_args* a = args[g];
     struct { float* seg_sumsq; float* scalars; } w{seg_sumsq[g], scalars[g]};
+    // aux gradients + optimizer step + operand refresh in two launches (fc_opt_fused) whenever nothing needs the whole
+    // gradient in memory before the step (no FedProx term, no clipping) — the production configuration
+    if (a->n_fused_a + a->n_fused_b > 0 && !m->precise && a->prox_mu <= 0.f && a->max_grad_norm <= 0.f &&
+        (a->optimizer == FC_OPT_ADAMW || a->optimizer == FC_OPT_SGD)) {
+      TRY(fc_opt_fused(a->params, a->grads, a->opt_state0, a->opt_state1, a->operands, a->fused_a, a->n_fused_a, a->fused_b,
+                       a->n_fused_b, a->aux_layers, a->fused_counters, a->optimizer, a->lr, a->beta1, a->beta2, a->eps,
+                       a->weight_decay, a->momentum, a->dampening, a->nesterov, a->step, device, stream));
+      continue;
+    }
     if (a->n_aux_layers > 0)
       TRY(fc_aux_grads(a->params, a->grads, a->aux_layers, a->n_aux_layers, a->n_aux_chunks, m->aux_trained, device, stream));
     // FedProx proximal term (fedproxclient.py:64-67): per-tensor un-squared L2 norms

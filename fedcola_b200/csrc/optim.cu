@@ -297,6 +297,125 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// ---- fused optimizer tail: aux gradients + optimizer step + bf16 operand refresh in two launches ------------------
+// The separate passes  aux_grads (dA = s*dW, ds = <dW, A>)  ->  AdamW/SGD over the arena  ->  prep_weights
+// (W_eff = W + s*A -> bf16)  collapse into
+//   phase A: every trainable tensor that is not a Linear weight.  An aux_weight chunk takes its gradient on the fly,
+//            s_old * dW (never materialised), and leaves its share of <dW, A> behind; the block that completes a
+//            layer's last chunk also steps that layer's cross_modal_scale (nobody reads s_old of that layer any more).
+//   phase B: the Linear weights.  Steps W and writes the bf16 GEMM operand bf16(W_new + s_new * A_new) from registers.
+// so CrossModalReparamLinear's mix (mome.py:58-60) and its autograd never run as elementwise kernels of their own.
+// Not used with gradient clipping or the FedProx term (both need every gradient in memory before the step).
+struct FChunk {
+  long long off;      // float offset of the chunk in the param / grad / state arenas
+  int len;            // <= kChunk
+  int kind;           // 0 plain | 1 aux_weight (phase A) | 2 Linear weight (phase B) | 3 Linear weight with an aux partner
+  int layer;          // kinds 1, 3: index into the aux layer table
+  int pad;
+  long long x0;       // kind 1: offset of the matching W element;  kinds 2, 3: bf16 element offset in the operand arena
+  long long x1;       // kind 3: offset of the matching aux_weight element
+};
+struct FAuxLayer {
+  long long w_off, a_off, s_off;
+  long long numel;
+  int chunk_start;    // (unused here: same table as fc_aux_grads)
+};
+struct OptHyper {
+  int opt;            // FC_OPT_ADAMW | FC_OPT_SGD
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;      // AdamW
+  float momentum, dampening;                            // SGD
+  int nesterov, first_step;
+};
+
+__device__ __forceinline__ float opt_step1(const OptHyper& h, float p, float g, float& m, float& v) {
+  if (h.opt == FC_OPT_ADAMW) {
+    const float w = p * (1.0f - h.lr * h.wd);
+    m = m + (g - m) * (1.0f - h.beta1);
+    v = v * h.beta2 + (1.0f - h.beta2) * g * g;
+    const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+    return w - (h.lr / h.bc1) * (m / denom);
+  }
+  if (h.wd != 0.0f) g += h.wd * p;
+  if (h.momentum != 0.0f) {
+    m = h.first_step ? g : h.momentum * m + (1.0f - h.dampening) * g;
+    g = h.nesterov ? g + h.momentum * m : m;
+  }
+  return p - h.lr * g;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(256) fused_opt_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, __nv_bfloat16* __restrict__ ops,
+                                                        const FChunk* __restrict__ chunks, int n_chunks,
+                                                        const FAuxLayer* __restrict__ layers, int* __restrict__ counters,
+                                                        const OptHyper h) {
+  __shared__ float s_red[8];
+  __shared__ int s_last;
+  const bool adam = h.opt == FC_OPT_ADAMW;
+  const bool use_m = adam || h.momentum != 0.0f;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const FChunk ch = chunks[c];
+    float s_scale = 0.f;                         // kind 1: s_old (gradient of A = s_old * dW); kind 3: s_new
+    if (ch.kind == 1 || ch.kind == 3) s_scale = p[layers[ch.layer].s_off];
+    float dot = 0.f;
+    for (int i = threadIdx.x * 4; i < ch.len; i += blockDim.x * 4) {
+      const long long o = ch.off + i;
+      float4 pv = ld4(p + o), gv, mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (PHASE == 0 && ch.kind == 1) {          // dA = s_old * dW, and this chunk's share of ds = <dW, A>
+        const float4 gw = ld4(g + ch.x0 + i);
+        dot += (gw.x * pv.x + gw.y * pv.y) + (gw.z * pv.z + gw.w * pv.w);
+        gv = make_float4(s_scale * gw.x, s_scale * gw.y, s_scale * gw.z, s_scale * gw.w);
+      } else {
+        gv = ld4(g + o);
+      }
+      if (use_m && !(h.opt == FC_OPT_SGD && h.first_step)) mv = ld4(m + o);
+      if (adam) vv = ld4(v + o);
+      float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pp[k] = opt_step1(h, pp[k], gp[k], mp[k], vp[k]);
+      st4(p + o, pv);
+      if (use_m) st4(m + o, mv);
+      if (adam) st4(v + o, vv);
+      if (PHASE == 1) {                          // the GEMM operand of this Linear: bf16(W_new [+ s_new * A_new])
+        float4 w = pv;
+        if (ch.kind == 3) {
+          const float4 av = ld4(p + ch.x1 + i);
+          w.x += s_scale * av.x; w.y += s_scale * av.y; w.z += s_scale * av.z; w.w += s_scale * av.w;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(ops + ch.x0 + i) = pk;
+      }
+    }
+    if (PHASE == 0 && ch.kind == 1) {            // CTA-uniform
+      dot = warp_sum(dot);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dot;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        const FAuxLayer L = layers[ch.layer];
+        atomicAdd(g + L.s_off, t);
+        __threadfence();
+        const int n_layer_chunks = (int)((L.numel + kChunk - 1) / kChunk);
+        s_last = atomicAdd(counters + ch.layer, 1) == n_layer_chunks - 1;
+        if (s_last) {                            // the layer's <dW, A> is complete: step its cross_modal_scale
+          __threadfence();
+          counters[ch.layer] = 0;                // re-armed for the next step
+          const float gs = *reinterpret_cast<volatile float*>(g + L.s_off);
+          float ms = use_m ? m[L.s_off] : 0.f, vs = adam ? v[L.s_off] : 0.f;
+          p[L.s_off] = opt_step1(h, p[L.s_off], gs, ms, vs);
+          if (use_m) m[L.s_off] = ms;
+          if (adam) v[L.s_off] = vs;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 int grid_for(int n_items, int device, int per_sm) {
   int g = fc_num_sms(device) * per_sm;
   return n_items < g ? n_items : g;
@@ -396,5 +515,38 @@ extern "C" int fc_colsum_bf16(const void* x, long long ld, int rows, int n, floa
   colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, n, rpb, out);
   FC_LAUNCH_CHECK();
+  return FC_OK;
+}
+
+// chunks_a / chunks_b: device arrays of {long long off; int len, kind, layer, pad; long long x0, x1;} (see FChunk);
+// aux_layers: as for fc_aux_grads; counters: n_aux_layers zeroed ints (left zero again on return).
+extern "C" int fc_opt_fused(float* params, float* grads, float* state0, float* state1, void* operands_bf16,
+                            const void* chunks_a, int n_chunks_a, const void* chunks_b, int n_chunks_b,
+                            const void* aux_layers, int* counters, int optimizer, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, float momentum, float dampening, int nesterov, int step,
+                            int device, void* stream) {
+  FC_REQUIRE(optimizer == FC_OPT_ADAMW || optimizer == FC_OPT_SGD, "fc_opt_fused: optimizer %d", optimizer);
+  FC_REQUIRE(step >= 1, "fc_opt_fused: step must be >= 1");
+  FC_REQUIRE(optimizer != FC_OPT_ADAMW || (state0 && state1), "fc_opt_fused: AdamW needs both moment arenas");
+  FC_REQUIRE(optimizer != FC_OPT_SGD || momentum == 0.0f || state0, "fc_opt_fused: momentum needs a buffer");
+  FcDeviceGuard guard(device);
+  OptHyper h;
+  h.opt = optimizer; h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = weight_decay;
+  h.bc1 = 1.0f - powf(beta1, (float)step);
+  h.bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  h.momentum = momentum; h.dampening = dampening; h.nesterov = nesterov; h.first_step = step == 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_chunks_a > 0) {
+    fused_opt_kernel<0><<<grid_for(n_chunks_a, device, 8), 256, 0, st>>>(
+        params, grads, state0, state1, reinterpret_cast<__nv_bfloat16*>(operands_bf16),
+        reinterpret_cast<const FChunk*>(chunks_a), n_chunks_a, reinterpret_cast<const FAuxLayer*>(aux_layers), counters, h);
+    FC_LAUNCH_CHECK();
+  }
+  if (n_chunks_b > 0) {
+    fused_opt_kernel<1><<<grid_for(n_chunks_b, device, 8), 256, 0, st>>>(
+        params, grads, state0, state1, reinterpret_cast<__nv_bfloat16*>(operands_bf16),
+        reinterpret_cast<const FChunk*>(chunks_b), n_chunks_b, reinterpret_cast<const FAuxLayer*>(aux_layers), counters, h);
+    FC_LAUNCH_CHECK();
+  }
   return FC_OK;
 }

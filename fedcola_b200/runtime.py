@@ -42,12 +42,16 @@ class StepArgs(ctypes.Structure):
                 ("img", c_vp), ("ids", c_vp), ("labels", c_vp), ("droppath", c_vp), ("stats", c_vp),
                 ("chunks", c_vp), ("n_chunks", c_int), ("n_segments", c_int),
                 ("prep_layers", c_vp), ("n_prep_layers", c_int), ("n_prep_tiles", c_int),
-                ("aux_layers", c_vp), ("n_aux_layers", c_int), ("n_aux_chunks", c_int)]
+                ("aux_layers", c_vp), ("n_aux_layers", c_int), ("n_aux_chunks", c_int),
+                ("fused_a", c_vp), ("n_fused_a", c_int), ("fused_b", c_vp), ("n_fused_b", c_int),
+                ("fused_counters", c_vp)]
 
 
 CHUNK_DT = np.dtype([("off", "<i8"), ("len", "<i4"), ("seg", "<i4")], align=True)
 PREP_DT = np.dtype([("w_off", "<i8"), ("a_off", "<i8"), ("s_off", "<i8"), ("dst_off", "<i8"), ("dstT_off", "<i8"),
                     ("rows", "<i4"), ("cols", "<i4"), ("tile_start", "<i4")], align=True)
+FCHUNK_DT = np.dtype([("off", "<i8"), ("len", "<i4"), ("kind", "<i4"), ("layer", "<i4"), ("pad", "<i4"), ("x0", "<i8"),
+                      ("x1", "<i8")], align=True)
 AUX_DT = np.dtype([("w_off", "<i8"), ("a_off", "<i8"), ("s_off", "<i8"), ("numel", "<i8"), ("chunk_start", "<i4")],
                   align=True)
 
@@ -146,6 +150,55 @@ class ModelPlan:
         t["len"] = np.minimum(self.chunk, nums[seg_id] - k * self.chunk)
         t["seg"] = seg_id
         cache[sig] = (t, len(segs))
+        return cache[sig]
+
+    def fused_tables(self, requires_grad):
+        """Chunk tables of the fused optimizer tail (fc_opt_fused): (phase A, phase B) or None when the combination of
+        frozen / trainable tensors is not one it covers (then the separate aux_grads / step / prep kernels run).
+        Cached per requires_grad signature."""
+        segs = [s for s in self.spec.unique_segments() if requires_grad.get(s.key, s.requires_grad)]
+        sig = tuple(s.key for s in segs)
+        cache = self.__dict__.setdefault("_fused_cache", {})
+        if sig in cache:
+            return cache[sig]
+        by_off = {s.offset: s for s in segs}
+        lin = {}          # W offset -> (operand offset, A offset, s offset, aux layer index)
+        aux_index = {int(r["w_off"]): i for i, r in enumerate(self.aux_table)}
+        for r in self.prep_table:
+            lin[int(r["w_off"])] = (int(r["dst_off"]), int(r["a_off"]), int(r["s_off"]), aux_index.get(int(r["w_off"]), -1))
+        a_of, s_of, ok = {}, set(), True
+        for w, (dst, a, s_, li) in lin.items():
+            if a >= 0:
+                # an aux layer is covered when W, aux_weight and cross_modal_scale all train (--aux_trained)
+                if not (w in by_off and a in by_off and s_ in by_off and li >= 0):
+                    ok = False
+                a_of[a] = (w, li)
+                s_of.add(s_)
+        if not ok:
+            cache[sig] = None
+            return None
+        rows_a, rows_b = [], []
+
+        def chunks(seg):
+            for k in range(0, seg.numel, self.chunk):
+                yield k, min(self.chunk, seg.numel - k)
+        for sg in segs:
+            if sg.offset in s_of:
+                continue                                   # stepped by the block that completes its layer's <dW, A>
+            if sg.offset in lin:
+                dst, a, s_, li = lin[sg.offset]
+                for k, n in chunks(sg):
+                    rows_b.append((sg.offset + k, n, 3 if a >= 0 else 2, max(li, 0), 0, dst + k, a + k if a >= 0 else 0))
+            elif sg.offset in a_of:
+                w, li = a_of[sg.offset]
+                for k, n in chunks(sg):
+                    rows_a.append((sg.offset + k, n, 1, li, 0, w + k, 0))
+            else:
+                for k, n in chunks(sg):
+                    rows_a.append((sg.offset + k, n, 0, 0, 0, 0, 0))
+        ta = np.array(rows_a, dtype=FCHUNK_DT) if rows_a else np.zeros(0, dtype=FCHUNK_DT)
+        tb = np.array(rows_b, dtype=FCHUNK_DT) if rows_b else np.zeros(0, dtype=FCHUNK_DT)
+        cache[sig] = (ta, tb)
         return cache[sig]
 
     def workspace_bytes(self, B):
@@ -384,6 +437,15 @@ class ClientTrainer:
         self.state0 = torch.zeros_like(model.arena) if (self.opt == OPT_ADAMW or momentum != 0.0) else None
         self.state1 = torch.zeros_like(model.arena) if self.opt == OPT_ADAMW else None
         self.stats = torch.zeros(4, dtype=torch.float32, device=rt.device)
+        # fused optimizer tail (aux gradients + step + bf16 operand refresh in two launches), when it applies
+        self.fused = None
+        ft = rt.plan.fused_tables(flags) if (not rt.plan.precise and max_grad_norm <= 0 and prox_mu <= 0) else None
+        if ft is not None:
+            fk = ("fused", id(ft), str(rt.device))
+            if fk not in cdev:
+                cdev[fk] = (_to_dev(ft[0], rt.device), _to_dev(ft[1], rt.device), len(ft[0]), len(ft[1]))
+            self.fused = cdev[fk]
+            self.fused_counters = torch.zeros(max(len(rt.plan.aux_table), 1), dtype=torch.int32, device=rt.device)
         self.step_count = 0
         self.global_arena = global_arena
         a = StepArgs()
@@ -420,6 +482,14 @@ class ClientTrainer:
         a.n_prep_layers, a.n_prep_tiles = len(p.prep_table), p.n_prep_tiles
         a.aux_layers = rt.aux_dev.data_ptr() if rt.aux_dev is not None else None
         a.n_aux_layers, a.n_aux_chunks = len(p.aux_table), p.n_aux_chunks
+        if self.fused is not None:
+            fa, fb, na, nb = self.fused
+            a.fused_a, a.n_fused_a = (fa.data_ptr() if fa is not None else None), na
+            a.fused_b, a.n_fused_b = (fb.data_ptr() if fb is not None else None), nb
+            a.fused_counters = self.fused_counters.data_ptr()
+        else:
+            a.fused_a = a.fused_b = a.fused_counters = None
+            a.n_fused_a = a.n_fused_b = 0
         self._keep = (img, ids, labels, droppath)      # the launch is asynchronous: keep the batch alive
         return B
 

@@ -233,6 +233,19 @@ int fc_prep_weights(const float* params, void* operands_bf16, const void* layers
 int fc_aux_grads(const float* params, float* grads, const void* layers, int n_layers, int n_chunks,
                  int aux_trained, int device, void* stream);
 int fc_colsum_bf16(const void* x, long long ld, int rows, int n, float* out, int device, void* stream);
+/* The optimizer tail in two launches instead of aux_grads -> step -> prep_weights (no clipping, no FedProx term):
+ * phase A steps every trainable tensor that is not a Linear weight — an aux_weight chunk takes its gradient s_old*dW on
+ * the fly and leaves its share of ds = <dW, A>; the block finishing a layer steps its cross_modal_scale — and phase B
+ * steps the Linear weights and writes the bf16 GEMM operand bf16(W_new + s_new*A_new) from registers.
+ *   chunks_a / chunks_b: device arrays of {long long off; int len, kind, layer, pad; long long x0, x1;}
+ *     kind 0 plain | 1 aux_weight (x0 = offset of the matching W element) | 2 Linear weight (x0 = operand element)
+ *     | 3 Linear weight with aux partner (x0 = operand element, x1 = offset of the matching aux_weight element);
+ *   aux_layers as for fc_aux_grads; counters: one zeroed int per aux layer (zero again on return).
+ * ref: src/models/mome.py:58-60 + autograd, src/client/fedavgclient.py:63,100. */
+int fc_opt_fused(float* params, float* grads, float* state0, float* state1, void* operands_bf16, const void* chunks_a,
+                 int n_chunks_a, const void* chunks_b, int n_chunks_b, const void* aux_layers, int* counters,
+                 int optimizer, float lr, float beta1, float beta2, float eps, float weight_decay, float momentum,
+                 float dampening, int nesterov, int step, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32-accurate validation mode (precision = 'fp32'): fp32 activations, split-operand GEMMs (fc_gemm_split), fp32 FMA
@@ -328,6 +341,10 @@ typedef struct {
   const void* chunks; int n_chunks; int n_segments;      /* trainable chunk table */
   const void* prep_layers; int n_prep_layers; int n_prep_tiles;
   const void* aux_layers; int n_aux_layers; int n_aux_chunks;
+  /* fused optimizer tail (fc_opt_fused); n_fused_a + n_fused_b == 0: the separate aux_grads / step / prep kernels */
+  const void* fused_a; int n_fused_a;
+  const void* fused_b; int n_fused_b;
+  int* fused_counters;
 } fc_step_args;
 
 int fc_client_step(const fc_mat_desc* m, const fc_step_args* a, int device, void* stream);
