@@ -230,6 +230,7 @@ def _to_dev(np_table, device):
 
 
 _PLAN_CACHE = {}
+_PLAN_LOCK = __import__("threading").Lock()      # client worker threads build their first runtime concurrently
 
 
 def plan_for(spec: MatSpec, precise=False) -> ModelPlan:
@@ -239,7 +240,10 @@ def plan_for(spec: MatSpec, precise=False) -> ModelPlan:
            spec.aux_trained, spec.aux_attn_only, spec.aux_mlp_only, spec.share_scope, tuple(spec.keys()))
     p = _PLAN_CACHE.get(sig)
     if p is None:
-        p = _PLAN_CACHE[sig] = ModelPlan(spec, precise)
+        with _PLAN_LOCK:
+            p = _PLAN_CACHE.get(sig)
+            if p is None:
+                p = _PLAN_CACHE[sig] = ModelPlan(spec, precise)
     return p
 
 

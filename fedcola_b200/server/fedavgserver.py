@@ -173,7 +173,12 @@ class FedavgServer(BaseServer):
         self.server_dataset = datasets[1]
 
     def _set_evaluator(self):
-        self.evaluator = None     # COCOEvaluator (retrieval recall@k) is outside the round hot path
+        """fedavgserver.py:177-181"""
+        from ..metrics import COCOEvaluator
+        evaluator = COCOEvaluator("matmul", n_crossfolds=5, extract_device=str(self.server_device),
+                                  eval_device=str(self.server_device), verbose=False)
+        evaluator.set_logger(logger)
+        self.evaluator = evaluator
 
     def _init_param_scope(self, shared_param, share_scope):
         names = []
@@ -333,6 +338,12 @@ class FedavgServer(BaseServer):
                 self._stream_pool[str(dev)].put(stream)
             out = []
             for client in group:
+                # only the arena has to survive until the aggregation: optimizer state, gradients, bf16 operands and
+                # the activation workspace (3x the arena + GBs of activations) go back to the allocator now, so a GPU
+                # can hold the arenas of dozens of sampled clients (BASELINE configs[3]: 64 ViT-B clients)
+                client.trainer = None
+                if client.model is not None:
+                    client.model._runtime = None
                 if not retain_model:
                     client.model = None
                 out.append(({client.id: len(client.training_set)}, {client.id: res[client.id]}))
@@ -533,23 +544,41 @@ class FedavgServer(BaseServer):
     # ---- evaluation (:677-757, 858-868) --------------------------------------------------------------------
     @torch.no_grad()
     def _central_evaluate(self, fedavg=False):
+        """fedavgserver.py:677-757: the global models on the server's test sets — uni-modal loss / acc1 through the native
+        forward in eval mode, image<->caption retrieval recall through COCOEvaluator."""
+        MM_METRICS = ("recall_1", "recall_5", "recall_10")
+        suffix = "after" if not fedavg else ""
         for dataset, server_dataset in self.server_dataset.items():
-            if DATASET_2_MODALITY[dataset] == "img+txt":
-                logger.warning(f"[{dataset}] retrieval evaluation (COCOEvaluator) is not part of the accelerated "
-                               "round path; skipped")
-                continue
             model = self.global_models[dataset]
+            if DATASET_2_MODALITY[dataset] == "img+txt":
+                self.evaluator.set_model(model)
+                kw = getattr(self.args, "retrieval_eval_kwargs", {})      # (fold sizes of small synthetic test sets)
+                result = self.evaluator.evaluate(torch.utils.data.DataLoader(dataset=server_dataset,
+                                                                             batch_size=self.args.eval_batch_size, shuffle=True),
+                                                 eval_batch_size=self.args.eval_batch_size, **kw)
+                res = {}
+                if "n_fold" in result:
+                    for t in ("i2t", "t2i"):
+                        for metric in MM_METRICS:
+                            res[f"Result/Server {dataset} 1k_{t}_{metric.title()}"] = result["n_fold"][t][metric]
+                    res[f"Test/Server {dataset} 1k_r@1sum"] = result["n_fold"]["t2i"]["recall_1"] + result["n_fold"]["i2t"]["recall_1"]
+                for t in ("i2t", "t2i"):
+                    for metric in MM_METRICS:
+                        res[f"Result/Server {dataset} 5k_{t}_{metric.title()}"] = result[t][metric]
+                res[f"Test/Server {dataset} 5k_r@1sum"] = result["t2i"]["recall_1"] + result["i2t"]["recall_1"]
+                self.writer.log(res, self.round)
+                self.results[self.round][f"server_evaluated_{dataset + suffix}"] = result
+                continue
             model.eval()
             loss_sum = correct = n = 0
             loader = torch.utils.data.DataLoader(dataset=server_dataset, batch_size=self.args.B, shuffle=False)
             for inputs, targets in loader:
                 inputs, targets = inputs.to(self.server_device), targets.to(self.server_device)
                 out = model([inputs, None])[0] if DATASET_2_MODALITY[dataset] == "img" else model([None, inputs])[1]
-                loss_sum += torch.nn.functional.cross_entropy(out, targets).item() * len(out)
+                loss_sum += torch.nn.functional.cross_entropy(out, targets).item() * len(out)     # MetricManager.track
                 correct += (out.argmax(1) == targets).sum().item()
                 n += len(out)
             result = {"loss": loss_sum / len(server_dataset), "metrics": {"acc1": correct / max(n, 1)}}
-            suffix = "after" if not fedavg else ""
             self.writer.log({f"Loss/Server {dataset + suffix} Loss": result["loss"]}, self.round)
             for name, value in result["metrics"].items():
                 self.writer.log({f"Test/Server {dataset + suffix} {name.title()}": value}, self.round)

@@ -207,6 +207,23 @@ class TensorItems(torch.utils.data.Dataset):
         return self.a[i], self.b[i]
 
 
+class RetrievalItems(torch.utils.data.Dataset):
+    """COCO/Flickr-style retrieval test set: `caps` captions per image, items (img, ids, image_id, ann_id, index) and the
+    attributes COCOEvaluator.extract_features reads (n_images, iid_to_cls)."""
+
+    def __init__(self, n_images, caps=5, seed=61, seq_len=TRAIN_SEQ, vocab=384):
+        rng = np.random.RandomState(seed)
+        self.imgs = torch.from_numpy(rng.standard_normal((n_images, 3, 224, 224)).astype(np.float32))
+        self.ids = torch.from_numpy(rng.randint(1, vocab, size=(n_images * caps, seq_len)).astype(np.int64))
+        self.caps, self.n_images, self.iid_to_cls = caps, n_images, None
+
+    def __len__(self):
+        return self.ids.shape[0]
+
+    def __getitem__(self, i):
+        return self.imgs[i // self.caps], self.ids[i], 1000 + i // self.caps, 5000 + i, i
+
+
 def subsample(a, step=13):
     return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])
 
