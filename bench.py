@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=3, help="client worker threads per GPU (args.num_thread)")
     ap.add_argument("--client-group", type=int, default=int(os.environ.get("FC_CLIENT_GROUP", 3)),
                     help="clients of one architecture trained in lockstep by shared kernel launches (1 = off)")
+    ap.add_argument("--host-profile", type=int, default=0, metavar="N",
+                    help="cProfile N rounds (workers inline) into gpurun_out/host_profile.txt; prints no bench line")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference arms: samples per client per step (0 = one batch)")
     ap.add_argument("--ref-budget-s", type=float, default=180.0, help="reference arm: stop timing new steps after this long")
@@ -325,6 +327,33 @@ def run_ours(a):
         server.update()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        return
+
+    if a.host_profile:  # where the interpreter's time goes in a round: cProfile over N rounds, workers run inline
+        import cProfile
+        import pstats
+        a.threads = 1
+        server, args = make_server("device")
+        for _ in range(3):
+            server.round += 1
+            server.update()
+        torch.cuda.synchronize()
+        prof = cProfile.Profile()
+        t0 = time.perf_counter()
+        prof.enable()
+        for _ in range(a.host_profile):
+            server.round += 1
+            server.update()
+        prof.disable()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / a.host_profile
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/host_profile.txt", "w") as f:
+            f.write(f"# {a.config}: {ms:.1f} ms per round with --threads 1 under cProfile, {a.host_profile} rounds\n")
+            st = pstats.Stats(prof, stream=f)
+            st.sort_stats("tottime").print_stats(45)
+            st.sort_stats("cumulative").print_stats(60)
+        print(f"host profile written ({ms:.1f} ms per round)", file=sys.stderr)
         return
 
     # ---- parity guard: the bounded sample of this workload through OUR server, losses kept for the check against

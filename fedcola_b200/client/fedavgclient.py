@@ -6,6 +6,7 @@ arena, csrc/mat_driver.cu) on the client's CUDA device; the model never leaves H
 aggregation, and the per-step `loss.item()` host sync of the reference (:102) is replaced by device-side
 accumulators read once per epoch."""
 import copy
+import threading
 import inspect
 import logging
 
@@ -199,6 +200,10 @@ def update_group(clients):
     return results
 
 
+_SHELL_LOCK = threading.Lock()
+_SHELL_POOL_MAX = 64          # model objects kept per global model (their arenas stay allocated)
+
+
 class FedavgClient(BaseClient):
     def __init__(self, args, training_set, test_set, task="cls", eval_metrics=["acc1"], modality="ct", writer=None,
                  criterion="CrossEntropyLoss"):
@@ -280,7 +285,35 @@ class FedavgClient(BaseClient):
         raise NotImplementedError("client-side evaluation is dead code in the reference (fedavgclient.py:118)")
 
     def download(self, models):
-        self.model = copy.deepcopy(models[self.dataset])       # D2D copy of the flat arena
+        """fedavgclient.py:156 `self.model = copy.deepcopy(models[self.dataset])`.  The copy is one D2D copy of the flat
+        arena; the model OBJECT (module tree + ~300 parameter views, ~15 ms of Python to build) is taken from the pool
+        of objects released at the end of earlier rounds (`release_model`) when one is free on this client's GPU, so
+        that a round's set-up does not leave the GPU waiting on the interpreter."""
+        src = models[self.dataset]
+        want = torch.device(self.device) if str(self.device).startswith("cuda") else src.device
+        if want.type == "cuda" and want.index is None:
+            want = torch.device("cuda", torch.cuda.current_device())
+        shell = None
+        with _SHELL_LOCK:
+            pool = src.__dict__.setdefault("_shell_pool", [])
+            for i, m in enumerate(pool):
+                if m.device == want:
+                    shell = pool.pop(i)
+                    break
+        self.model = shell.refill_from(src) if shell is not None else copy.deepcopy(src)
+
+    def release_model(self, models):
+        """Hand the model object back for reuse by a later `download` (called by the server when it drops the clients'
+        models at the end of a round); the pool keeps at most one round's worth of objects per global model."""
+        m, self.model = self.model, None
+        src = models.get(self.dataset) if m is not None else None
+        if src is None or getattr(m, "spec", None) is None or m.spec.signature != src.spec.signature:
+            return
+        m._runtime = None
+        with _SHELL_LOCK:
+            pool = src.__dict__.setdefault("_shell_pool", [])
+            if len(pool) < _SHELL_POOL_MAX and all(m is not x for x in pool):
+                pool.append(m)
 
     def upload(self):
         """state_dict with the aux branch merged (W + A*s) and aux keys removed (:158-184).  API-compat view:

@@ -138,11 +138,12 @@ class ModalityAgnosticTransformer(nn.Module):
         new = ModalityAgnosticTransformer.__new__(ModalityAgnosticTransformer)
         nn.Module.__init__(new)
         for k, v in self.__dict__.items():
-            if k in ("_parameters", "_buffers", "_modules", "_arena", "_runtime", "_params_by_key") or \
+            if k in ("_parameters", "_buffers", "_modules", "_arena", "_runtime", "_params_by_key", "_shell_pool") or \
                     k.startswith("_forward") or k.startswith("_backward") or k.startswith("_state_dict") or \
                     k.startswith("_load_state_dict"):
                 continue
-            new.__dict__[k] = copy.deepcopy(v, memo)
+            # the spec is immutable once the model is built (sync_shared_weights runs in __init__), so copies share it
+            new.__dict__[k] = v if k == "spec" else copy.deepcopy(v, memo)
         new._arena = self._arena.clone()
         new._runtime = None
         new._bind()
@@ -150,6 +151,23 @@ class ModalityAgnosticTransformer(nn.Module):
             new._params_by_key[k].requires_grad_(p.requires_grad)
         new.training = self.training
         return new
+
+    def refill_from(self, other):
+        """Make this model a copy of `other` (same spec) without rebuilding the module tree: one arena copy (device to
+        device, also across GPUs) plus the requires_grad flags and the training flag.  What `copy.deepcopy(other)`
+        yields, for a model object that is being reused (client/fedavgclient.py::download)."""
+        if other.spec is not self.spec and other.spec.signature != self.spec.signature:
+            raise ValueError("refill_from: the two models differ in architecture")
+        self._arena.copy_(other._arena, non_blocking=True)
+        mine = self._params_by_key
+        for k, p in other._params_by_key.items():
+            q = mine[k]
+            if q.requires_grad != p.requires_grad:
+                q.requires_grad_(p.requires_grad)
+            q.grad = None
+        self._runtime = None
+        self.train(other.training)
+        return self
 
     @property
     def arena(self):

@@ -488,6 +488,8 @@ class FedavgServer(BaseServer):
         # the reference runs gc.collect() per client here (1.2 s of a 3.2 s CPU round); the flat
         # arenas have no reference cycles, so dropping the references frees them immediately
         for client in self.clients:
+            if client.model is not None:
+                client.release_model(self.global_models)     # the object is reused by a later download()
             client.model = None
             client.trainer = None
 

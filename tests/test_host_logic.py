@@ -135,3 +135,53 @@ def test_attention_bias_gradient_identities():
     assert k.grad.sum(2).abs().max() < 1e-12 * k.grad.abs().max() * N
     # and the Q third is what the kernel reduces explicitly: nothing special about it
     assert q.grad.sum(2).abs().max() > 1e-3
+
+
+def test_download_reuses_released_model_objects():
+    """client.download() is `copy.deepcopy(models[dataset])` (fedavgclient.py:156); a model object released at the end of
+    a round is refilled instead of rebuilt, and must be indistinguishable from a fresh deep copy: same values, same
+    requires_grad flags, same training flag, no gradients, no shared storage with the global model."""
+    import copy
+    import types
+    from fedcola_b200.client.fedavgclient import FedavgClient
+    from fedcola_b200.models.mome import ModalityAgnosticTransformer
+    torch.manual_seed(0)
+    g = ModalityAgnosticTransformer(img_size=32, patch_size=16, embed_dim=32, depth=2, num_heads=2, modalities=["img", None],
+                                    num_classes=[10, None], tasks=["cls", None], with_aux=True)
+    c = FedavgClient.__new__(FedavgClient)
+    c.dataset, c.device, c.model = "CIFAR100", "cpu", None
+    models = {"CIFAR100": g}
+    c.download(models)
+    first = c.model
+    assert first is not g and first.spec is g.spec
+    assert first.arena.data_ptr() != g.arena.data_ptr() and torch.equal(first.arena, g.arena)
+    # train the copy a bit, leave junk behind, then hand it back
+    first.arena.add_(1.0)
+    next(iter(first.parameters())).grad = torch.ones_like(next(iter(first.parameters())))
+    for p in first.parameters():
+        p.requires_grad_(False)
+    first.eval()
+    c.release_model(models)
+    assert c.model is None and g._shell_pool == [first]
+    # the global moves on; one block gets frozen on the server side
+    g.arena.mul_(0.5)
+    frozen = [k for k in g._params_by_key if k.startswith("blockses.0.1.")]
+    for k in frozen:
+        g._params_by_key[k].requires_grad_(False)
+    g.train()
+    c.download(models)
+    assert c.model is first and g._shell_pool == []
+    fresh = copy.deepcopy(g)
+    assert torch.equal(c.model.arena, fresh.arena)
+    assert c.model.training == fresh.training
+    assert all(p.grad is None for p in c.model.parameters())
+    for (k, p), (k2, q) in zip(c.model.named_parameters(), fresh.named_parameters()):
+        assert k == k2 and p.requires_grad == q.requires_grad and torch.equal(p, q)
+    assert not hasattr(fresh, "_shell_pool") or "_shell_pool" not in fresh.__dict__
+    # a different architecture is never pooled under this global
+    other = ModalityAgnosticTransformer(img_size=32, patch_size=16, embed_dim=32, depth=1, num_heads=2, modalities=["img", None],
+                                        num_classes=[10, None], tasks=["cls", None])
+    c2 = FedavgClient.__new__(FedavgClient)
+    c2.dataset, c2.device, c2.model = "CIFAR100", "cpu", other
+    c2.release_model(models)
+    assert c2.model is None and g._shell_pool == []
