@@ -57,6 +57,8 @@ def parse_args():
                     help="clients of one architecture trained in lockstep by shared kernel launches (1 = off)")
     ap.add_argument("--host-profile", type=int, default=0, metavar="N",
                     help="cProfile N rounds (workers inline) into gpurun_out/host_profile.txt; prints no bench line")
+    ap.add_argument("--timeline", action="store_true",
+                    help="CUPTI kernel timeline of one round into gpurun_out/timeline.txt (GPU busy/idle, per-kernel sums)")
     ap.add_argument("--profile", action="store_true", help="one warm + one cudaProfiler-bracketed round (for ncu)")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference arms: samples per client per step (0 = one batch)")
     ap.add_argument("--ref-budget-s", type=float, default=180.0, help="reference arm: stop timing new steps after this long")
@@ -354,6 +356,58 @@ def run_ours(a):
             st.sort_stats("tottime").print_stats(45)
             st.sort_stats("cumulative").print_stats(60)
         print(f"host profile written ({ms:.1f} ms per round)", file=sys.stderr)
+        return
+
+    if a.timeline:      # CUPTI kernel timeline of one round (torch.profiler): busy / idle time of the GPU, per-kernel sums
+        from torch.profiler import profile, ProfilerActivity
+        server, args = make_server("device")
+        for _ in range(3):
+            server.round += 1
+            server.update()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            t0 = time.perf_counter()
+            server.round += 1
+            server.update()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+        ev = [(e.time_range.start, e.time_range.end, e.name, getattr(e, "stream", None)) for e in prof.events()
+              if str(getattr(e, "device_type", "")).endswith("CUDA") and e.time_range.end > e.time_range.start]
+        ev.sort()
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/timeline.txt", "w") as f:
+            if not ev:
+                f.write("no device events captured\n")
+                return
+            first, last = ev[0][0], max(e[1] for e in ev)
+            busy, cur_s, cur_e, gaps = 0.0, ev[0][0], ev[0][1], []
+            for s0, e0, _, _ in ev[1:]:
+                if s0 > cur_e:
+                    busy += cur_e - cur_s
+                    gaps.append((s0 - cur_e, cur_e - first))
+                    cur_s, cur_e = s0, e0
+                else:
+                    cur_e = max(cur_e, e0)
+            busy += cur_e - cur_s
+            span = last - first
+            f.write(f"# {a.config}: one round, wall {wall:.1f} ms (profiler attached); device span {span/1e3:.1f} ms, "
+                    f"busy (union over streams) {busy/1e3:.1f} ms, idle {(span-busy)/1e3:.1f} ms in {len(gaps)} gaps\n")
+            for lo, hi in ((0, 5), (5, 20), (20, 100), (100, 1000), (1000, 1e9)):
+                sel = [g for g, _ in gaps if lo <= g < hi]
+                f.write(f"gaps {lo:>5}-{hi:<10g} us: {len(sel):6d}  total {sum(sel)/1e3:8.2f} ms\n")
+            f.write("largest gaps (us, at ms into the round): " +
+                    ", ".join(f"{g:.0f}@{t/1e3:.1f}" for g, t in sorted(gaps, reverse=True)[:24]) + "\n")
+            per = {}
+            for s0, e0, name, _ in ev:
+                d = per.setdefault(name[:90], [0, 0.0])
+                d[0] += 1
+                d[1] += e0 - s0
+            tot = sum(v[1] for v in per.values())
+            f.write(f"sum of kernel durations {tot/1e3:.1f} ms over {len(ev)} device activities "
+                    f"(overlap factor {tot/busy:.2f})\n")
+            for name, (n, t) in sorted(per.items(), key=lambda kv: -kv[1][1])[:40]:
+                f.write(f"{100*t/tot:6.2f}% {t/1e3:9.3f} ms {n:6d} x {t/n:8.2f} us  {name}\n")
+        print("timeline written", file=sys.stderr)
         return
 
     # ---- parity guard: the bounded sample of this workload through OUR server, losses kept for the check against

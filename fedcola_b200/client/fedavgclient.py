@@ -82,13 +82,21 @@ class _ClientData:
         cudaMemcpyAsync per run of consecutive rows), so the copies hide under compute and only two batches of
         inputs ever occupy HBM."""
         if self.cols is not None and self.resident == "device":
+            # the epoch's row indices go up once, from pinned memory: a per-batch upload from a Python list is a
+            # pageable copy, which makes the host wait for the stream to drain before every step
+            flat = torch.tensor([i for idx in batches for i in idx], dtype=torch.int64)
+            if torch.cuda.is_available():
+                flat = flat.pin_memory()
+            flat = flat.to(self.cols[0].device, non_blocking=True)
+            at = 0
             for idx in batches:
                 contiguous = len(idx) > 0 and idx == list(range(idx[0], idx[0] + len(idx)))
                 if contiguous:
                     yield [c[idx[0]:idx[0] + len(idx)] for c in self.cols]
                 else:
-                    ix = torch.as_tensor(idx, device=self.cols[0].device)
+                    ix = flat[at:at + len(idx)]
                     yield [c.index_select(0, ix) for c in self.cols]
+                at += len(idx)
             return
         if not batches:
             return

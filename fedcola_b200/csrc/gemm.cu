@@ -136,6 +136,67 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
   const float tail = 0.5f * t * poly * e;                         // = 0.5*(1 - erf(z)) = Phi(-|x|), no cancellation
   cdf = x >= 0.0f ? 1.0f - tail : tail;
 }
+// ---- packed fp32 pairs: FFMA2 / FMUL2 / FADD2 do two fp32 lanes per issue slot (sm_100+).  The GELU epilogue is
+// bound by instruction issue (16 warps x ~20 instructions per element against a 2304-cycle main loop at K = 384),
+// so its arithmetic runs on pairs of adjacent accumulator columns.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_all(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// GELU of two adjacent columns: g = x*Phi(x), d = gelu'(x) = Phi(x) + x*phi(x).  Same Abramowitz-Stegun form as
+// gelu_parts (coefficients pre-multiplied by 0.5; Phi(x) = 0.5 + copysign(0.5 - Phi(-|x|), x)).
+__device__ __forceinline__ void gelu_pair(float x0, float x1, uint64_t& g, uint64_t& d) {
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t den = f2_fma(f2_pack(fabsf(x0), fabsf(x1)), f2_all(0.3275911f * 0.70710678118654752440f), f2_all(1.0f));
+  const uint64_t arg = f2_mul(f2_mul(x, x), f2_all(-0.5f * 1.4426950408889634f));
+  float d0, d1, a0, a1, t0, t1, e0, e1;
+  f2_unpack(den, d0, d1);
+  f2_unpack(arg, a0, a1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t t = f2_pack(t0, t1), e = f2_pack(e0, e1);
+  uint64_t poly = f2_fma(t, f2_all(0.5f * 1.061405429f), f2_all(0.5f * -1.453152027f));
+  poly = f2_fma(t, poly, f2_all(0.5f * 1.421413741f));
+  poly = f2_fma(t, poly, f2_all(0.5f * -0.284496736f));
+  poly = f2_fma(t, poly, f2_all(0.5f * 0.254829592f));
+  const uint64_t tail = f2_mul(f2_mul(t, poly), e);                 // Phi(-|x|) in [0, 0.5]
+  const uint64_t half_m = f2_fma(tail, f2_all(-1.0f), f2_all(0.5f)); // 0.5 - Phi(-|x|) >= 0
+  float h0, h1;
+  f2_unpack(half_m, h0, h1);
+  h0 = __uint_as_float(__float_as_uint(h0) | (__float_as_uint(x0) & 0x80000000u));
+  h1 = __uint_as_float(__float_as_uint(h1) | (__float_as_uint(x1) & 0x80000000u));
+  const uint64_t cdf = f2_add(f2_pack(h0, h1), f2_all(0.5f));
+  g = f2_mul(x, cdf);
+  d = f2_fma(f2_mul(x, e), f2_all(0.39894228040143267794f), cdf);
+}
+__device__ __forceinline__ uint32_t pack_bf16_f2(uint64_t v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -381,12 +442,10 @@ __device__ __forceinline__ void epilogue_tma_chunk(const GemmParams& p, const Gr
       uint32_t dp[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float c0, e0, c1, e1;
-        const float x0 = acc[8 * j + 2 * k], x1 = acc[8 * j + 2 * k + 1];
-        gelu_parts(x0, c0, e0);
-        gelu_parts(x1, c1, e1);
-        gp[4 * j + k] = pack_bf16(x0 * c0, x1 * c1);
-        dp[k] = pack_bf16(fmaf(x0 * 0.39894228040143267794f, e0, c0), fmaf(x1 * 0.39894228040143267794f, e1, c1));
+        uint64_t g2, d2;
+        gelu_pair(acc[8 * j + 2 * k], acc[8 * j + 2 * k + 1], g2, d2);
+        gp[4 * j + k] = pack_bf16_f2(g2);
+        dp[k] = pack_bf16_f2(d2);
       }
       sts_u4(swz128(buf, t, j), dp[0], dp[1], dp[2], dp[3]);
     }
