@@ -30,10 +30,13 @@ using namespace sm100;
 constexpr int HD = 64;
 constexpr int TILE = 128 * 128;            // bytes of one 128-row x 128-byte swizzled tile (16 KB)
 #ifdef FC_ATTN_PROF
+__device__ long long g_attn_bprof[2][32 * 16];      // backward: [0] elementwise warp 0, [1] control lane; 32 chunks x 16 stamps
+#define BPROF(who, chunk, slot) do { if (blockIdx.x == 0 && (chunk) < 32) g_attn_bprof[who][(chunk) * 16 + (slot)] = clock64(); } while (0)
 __device__ long long g_attn_prof[16 * 12];
 #define PROF(slot) do { if (threadIdx.x == 0 && T < 16) prof_s[T * 12 + (slot)] = clock64(); } while (0)
 #else
 #define PROF(slot) do { } while (0)
+#define BPROF(who, chunk, slot) do { } while (0)
 #endif
 #ifdef FC_ATTN_PROF
 constexpr int kMaxDynSmem = 232448 - 2048;
@@ -396,11 +399,13 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
 // D[q] = <dO[q], O[q]> and lse2[q] = lse[q]*log2(e) are computed from global memory one item ahead.
 // The qkv bias gradient is taken in the accumulator epilogues: the Q third by one warp reduction per item, the V
 // third from an all-ones row of P^T (sum_k dV = sum_q dO), the K third is identically zero.
-constexpr int kBwdThreads = (kSoftmaxWarps + 1) * 32;
+constexpr int kVecWarps = 2;                // warps that compute lse2 / D of the next item while this one runs
+constexpr int kBwdThreads = (kSoftmaxWarps + 1 + kVecWarps) * 32;
 constexpr int kRing = 4;                   // dS^T tiles (64 queries each): two pairs in flight
 
 struct BwdMaps {
   CUtensorMap qkv_a, qkv_b, do_a, do_b;      // box rows RA / RB
+  CUtensorMap dqkv_st;                       // gradient store: box = 64 columns x RA rows (rows past N are clipped)
 };
 struct BwdGroups {
   BwdMaps maps[MAXG];
@@ -411,8 +416,10 @@ struct BwdGroups {
   float* dbias[MAXG];
 };
 
+template <bool ONE_CHUNK>                   // ONE_CHUNK: N <= 64, an item is a single chunk (own flush path, own code)
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_per_group, int N, int H, float scale) {
+attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_per_group, int N, int H, float scale,
+                   int staged) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   const int RA = N > 128 ? 128 : ((N + 15) & ~15);
@@ -421,22 +428,32 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
   const int nkt = RB ? 2 : 1;                 // key tiles
   const int nqc = (NK + 63) >> 6;             // query chunks per key tile
   const int op_bytes = NK * 128;
-  // smem: Q | K | V | dO | dS^T ring | lse2,D vectors [2 items][2][256] | barriers
-  const uint32_t sQ = smem_u32(smem), sK = sQ + op_bytes, sV = sK + op_bytes, sDO = sV + op_bytes;
-  const uint32_t sRing = sDO + op_bytes;
-  uint8_t* vec_base = smem + 4 * op_bytes + kRing * TILE;
-  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(vec_base + 4096);
-  uint64_t* sdp_full = tma_bar + 1;           // [2] S^T/dP^T chunk buffer written
+  // One key tile (N <= 128): the operands are small, so there are TWO operand sets and item k+1 loads while item k
+  // computes.  Two key tiles: one set, reloaded piecewise as its parts die (see the control warp).
+  const int nsets = nkt == 1 ? 2 : 1;
+  // smem: nsets x (Q | K | V | dO) | dS^T ring | lse2,D vectors [2 items][2][256] | barriers
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sRing = sQ + nsets * 4 * op_bytes;
+  // staged: two more tiles through which dV/dK and dQ leave as TMA stores (when they fit, see the host side)
+  uint8_t* stage_ptr = smem + nsets * 4 * op_bytes + kRing * TILE;
+  const uint32_t sStage = sRing + kRing * TILE;
+  uint8_t* vec_base = stage_ptr + staged * TILE;        // staged = number of staging tiles: 0, 2 or 3
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(vec_base + 4096);   // [3] operand pieces / operand sets
+  uint64_t* sdp_full = tma_bar + 3;           // [2] S^T/dP^T chunk buffer written
   uint64_t* e_done = sdp_full + 2;            // [2] chunk consumed: P^T in TMEM, dS^T in smem          (16 arrivals)
   uint64_t* pair_done = e_done + 2;           // [2] dK/dQ (and every earlier MMA) of a pair completed
   uint64_t* acc_free = pair_done + 2;         //     dV/dK of a key tile read out of TMEM                (16 arrivals)
   uint64_t* dq_free = acc_free + 1;           //     dQ of an item read out of TMEM                      (16 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+  uint64_t* vec_full = dq_free + 1;           // [2] lse2 / D vectors of an item written                 (kVecWarps arrivals)
+  uint64_t* vec_free = vec_full + 2;          // [2] ... and no longer read by the elementwise warps     (16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vec_free + 2);
   const int d = H * HD, d3 = 3 * d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(tma_bar, 1);
+    mbar_init(&tma_bar[0], 1);
+    mbar_init(&tma_bar[1], 1);
+    mbar_init(&tma_bar[2], 1);
     mbar_init(&sdp_full[0], 1);
     mbar_init(&sdp_full[1], 1);
     mbar_init(&e_done[0], kSoftmaxWarps);
@@ -445,6 +462,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
     mbar_init(&pair_done[1], 1);
     mbar_init(acc_free, kSoftmaxWarps);
     mbar_init(dq_free, kSoftmaxWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&vec_full[i], kVecWarps);
+      mbar_init(&vec_free[i], kSoftmaxWarps);
+    }
     fence_barrier_init();
   }
   if (warp == kSoftmaxWarps) {
@@ -456,8 +477,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+  // a CTA takes a contiguous run of items: consecutive items are the heads of one sample (the same token rows of
+  // O / dO / qkv, the same pages), which keeps the per-item global reads of the elementwise warps short
+  const int first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_items / gridDim.x), stride = 1;
+  const int n_my = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_items / gridDim.x) - first;
   const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;
   // item -> (client group, sample, head)
   auto item_bh = [&](int item, int& cg, int& b, int& h) {
@@ -469,96 +492,268 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
   const bool has_dbias = G.dbias[0] != nullptr;       // (all groups agree: checked by the host)
 
   if (warp == kSoftmaxWarps) {
-    // ================= control warp: TMA producer + MMA issuer (one lane) =================
-    if (lane == 0 && n_my > 0) {
+    // ================= control warp: TMA producer + MMA issuer =================
+    // The whole warp runs the control flow (uniform values -> the descriptors live in uniform registers) and only
+    // the TMA / MMA / commit instructions are predicated on the elected lane.  Issuing from inside an `if (lane == 0)`
+    // branch makes the compiler wrap every tcgen05.mma in an ELECT / BRA.U.ANY loop: >= 46-77 cycles per
+    // instruction against the 32 (A in TMEM) - 48 (A in shared memory) cycles an M=128, N=64 MMA needs
+    // (tools/mma_probe.cu) — the backward issues ~140 of them per item.
+    if (n_my > 0) {
+      const bool leader = elect_one();
       for (int g = 0; g * items_per_group < n_items; ++g) {
-        prefetch_tmap(&G.maps[g].qkv_a);
-        prefetch_tmap(&G.maps[g].qkv_b);
-        prefetch_tmap(&G.maps[g].do_a);
-        prefetch_tmap(&G.maps[g].do_b);
+        if (leader) {
+          prefetch_tmap(&G.maps[g].qkv_a);
+          prefetch_tmap(&G.maps[g].qkv_b);
+          prefetch_tmap(&G.maps[g].do_a);
+          prefetch_tmap(&G.maps[g].do_b);
+        }
       }
       const uint32_t idesc_dv = umma_idesc_bf16(128, HD, 0, 1);    // A K-major (TMEM / dS^T tile), B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // A = dS^T tile read MN-major, B MN-major
-      auto load_item = [&](int item, bool prefetch_only) {
+      // Operand pieces, each with its own barrier, so that the next item's operands arrive while this item computes:
+      //   one key tile : piece 0 = the whole item, into operand set (k & 1)                      [bar = set]
+      //   two key tiles: piece 0 = K,V rows [0,128)   dead once the last pair of key tile 0 has completed
+      //                  piece 1 = Q,dO rows [0,128)  dead once the first pair of key tile 1 has completed
+      //                  piece 2 = rows [128,NK) of all four: dead with the item's last pair; first needed by chunk 2
+      auto load_piece = [&](int item, int piece, uint64_t* bar, uint8_t* base) {
         int cg, b, h;
         item_bh(item, cg, b, h);
         const BwdMaps& maps = G.maps[cg];
-        if (!prefetch_only) mbar_arrive_expect_tx(tma_bar, 4 * op_bytes);
+        if (leader) mbar_arrive_expect_tx(bar, nkt == 1 ? 4 * op_bytes : (piece == 2 ? 4 * RB * 128 : 2 * RA * 128));
         for (int op = 0; op < 4; ++op) {      // Q, K, V (columns of qkv), dO
-          const CUtensorMap* ma = op < 3 ? &maps.qkv_a : &maps.do_a;
-          const CUtensorMap* mb = op < 3 ? &maps.qkv_b : &maps.do_b;
+          const bool kv = op == 1 || op == 2;
+          if (nkt == 2 && ((piece == 0 && !kv) || (piece == 1 && kv))) continue;
           const int col = (op < 3 ? op * d : 0) + h * HD;
-          if (prefetch_only) {
-            tma_prefetch_3d(ma, col, 0, b);
-            if (RB) tma_prefetch_3d(mb, col, 128, b);
-          } else {
-            tma_load_3d(smem + op * op_bytes, ma, tma_bar, col, 0, b);
-            if (RB) tma_load_3d(smem + op * op_bytes + RA * 128, mb, tma_bar, col, 128, b);
-          }
+          if (!leader) continue;
+          if (nkt == 1 || piece < 2) tma_load_3d(base + op * op_bytes, op < 3 ? &maps.qkv_a : &maps.do_a, bar, col, 0, b);
+          else tma_load_3d(base + op * op_bytes + RA * 128, op < 3 ? &maps.qkv_b : &maps.do_b, bar, col, 128, b);
+        }
+      };
+      auto prefetch_item = [&](int item) {    // into L2 only
+        int cg, b, h;
+        item_bh(item, cg, b, h);
+        const BwdMaps& maps = G.maps[cg];
+        for (int op = 0; op < 4; ++op) {
+          const int col = (op < 3 ? op * d : 0) + h * HD;
+          if (!leader) continue;
+          tma_prefetch_3d(op < 3 ? &maps.qkv_a : &maps.do_a, col, 0, b);
+          if (RB) tma_prefetch_3d(op < 3 ? &maps.qkv_b : &maps.do_b, col, 128, b);
         }
       };
       int cc = 0, pair = 0, tile_ctr = 0;     // global chunk / pair / key-tile counters
+      // A tcgen05.mma of this size costs >= ~48 cycles whatever N is (tools/mma_probe.cu), and every instruction the
+      // issuing lane executes between two MMAs adds to that: no divisions, descriptors by addition, unrolled groups.
       const uint64_t dk0 = desc_k(0), dmn0 = desc_mn(0), dq0 = umma_smem_desc(0, TILE, 1024);
-      const uint64_t dK = desc_at(dk0, sK), dQ = desc_at(dk0, sQ), dV = desc_at(dk0, sV), dDO = desc_at(dk0, sDO);
-      auto issue_sdp = [&](int lc, int gc) {  // chunk lc of the item -> chunk buffer gc & 1
-        const int kt = lc / nqc, qc = lc - kt * nqc;
-        const int W = min(64, NK - 64 * qc);
-        const uint32_t idesc = umma_idesc_bf16(128, W, 0, 0);
+      // operand set in use: K-major descriptors (S^T / dP^T operands) and MN-major ones (B of dV, dK, dQ)
+      uint64_t dK = 0, dQ = 0, dV = 0, dDO = 0, mQ = 0, mK = 0, mDO = 0;
+      auto bind_ahead = [&](int set) {        // operands of S^T / dP^T (these run up to one item ahead)
+        const uint32_t q = sQ + set * 4 * op_bytes;
+        dQ = desc_at(dk0, q);
+        dK = desc_at(dk0, q + op_bytes);
+        dV = desc_at(dk0, q + 2 * op_bytes);
+        dDO = desc_at(dk0, q + 3 * op_bytes);
+      };
+      auto bind_cur = [&](int set) {          // B operands of dV / dK / dQ of the item being consumed
+        const uint32_t q = sQ + set * 4 * op_bytes;
+        mQ = desc_at(dmn0, q);
+        mK = desc_at(dmn0, q + op_bytes);
+        mDO = desc_at(dmn0, q + 3 * op_bytes);
+      };
+      bind_ahead(0);
+      bind_cur(0);
+      const int w_last = NK - 64 * (nqc - 1);                           // queries in the last chunk (16..64)
+      const uint32_t idesc_full = umma_idesc_bf16(128, 64, 0, 0), idesc_last = umma_idesc_bf16(128, w_last, 0, 0);
+      const int wp16_last = (NK - 128 * ((nqc - 1) >> 1)) >> 4;         // 16-query steps of the last pair (1..8)
+      int a_kt = 0, a_qc = 0;                 // the next chunk issue_sdp will compute (cursor inside the item)
+      auto issue_sdp = [&](int gc) {          // -> chunk buffer gc & 1
+        const uint32_t idesc = a_qc == nqc - 1 ? idesc_last : idesc_full;
         const uint32_t tb = tmem + (gc & 1) * 128;
-        const uint32_t kr = (kt * TILE) >> 4, qr = (qc * 64 * 128) >> 4;
+        const uint64_t ak = dK + a_kt * (TILE >> 4), av = dV + a_kt * (TILE >> 4);
+        const uint64_t bq = dQ + a_qc * 512, bd = dDO + a_qc * 512;       // 64 rows x 128 B = 512 x 16 B
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tb, dK + kr + 2 * j, dQ + qr + 2 * j, idesc, j > 0);
+        for (int j = 0; j < 4; ++j) if (leader) umma_bf16(tb, ak + 2 * j, bq + 2 * j, idesc, j > 0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tb + 64, dV + kr + 2 * j, dDO + qr + 2 * j, idesc, j > 0);
-        umma_commit(&sdp_full[gc & 1]);
+        for (int j = 0; j < 4; ++j) if (leader) umma_bf16(tb + 64, av + 2 * j, bd + 2 * j, idesc, j > 0);
+        if (leader) umma_commit(&sdp_full[gc & 1]);
+        if (++a_qc == nqc) {
+          a_qc = 0;
+          ++a_kt;
+        }
       };
       const int chunks = nkt * nqc;
-      for (int k = 0; k < n_my; ++k) {
-        if (k > 0) mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);   // operands of item k-1 are dead
-        load_item(first + k * stride, false);
-        if (k + 1 < n_my) load_item(first + (k + 1) * stride, true);
-        mbar_wait(tma_bar, k & 1);
+      // the first two chunks of item k: what they read (the item's set, or pieces 0 and 1) has been requested earlier
+      auto start_item = [&](int k) {
+        if (nkt == 1) {
+          mbar_wait(&tma_bar[k & 1], (k >> 1) & 1);
+          bind_ahead(k & 1);
+        } else {
+          mbar_wait(&tma_bar[0], k & 1);
+          mbar_wait(&tma_bar[1], k & 1);
+        }
         tc_fence_after();
-        issue_sdp(0, cc);
-        if (chunks > 1) issue_sdp(1, cc + 1);
-        for (int lc = 0; lc < chunks; ++lc, ++cc) {
-          const int kt = lc / nqc, qc = lc - kt * nqc;
-          const int W = min(64, NK - 64 * qc);
-          mbar_wait(&e_done[cc & 1], (cc >> 1) & 1);
-          tc_fence_after();
-          if (qc == 0 && tile_ctr > 0) mbar_wait(acc_free, (tile_ctr - 1) & 1);   // dV/dK of the previous tile read
-          // dV[kt] += P^T dO[chunk]   (A: packed P^T in this chunk's S^T columns, 8 columns per 16 queries)
-          const uint32_t tb = tmem + (cc & 1) * 128;
-          {
-            uint64_t b = desc_at(dmn0, sDO + 64 * qc * 128);
-            for (int j = 0; j < (W >> 4); ++j, b += 128) umma_bf16_ts(tDV, tb + 16 * j, b, idesc_dv, (qc | j) != 0);
+        a_kt = 0;
+        a_qc = 0;
+        issue_sdp(cc);
+        if (chunks > 1) issue_sdp(cc + 1);
+      };
+      // one key tile (two operand sets): S^T / dP^T of item k+1 are issued while item k is still being consumed —
+      // chunk c of item k+1 as soon as the chunk buffer it needs is free
+      auto open_next = [&](int k1) {
+        mbar_wait(&tma_bar[k1 & 1], (k1 >> 1) & 1);
+        tc_fence_after();
+        bind_ahead(k1 & 1);
+        a_kt = 0;
+        a_qc = 0;
+      };
+      if (n_my > 0) {
+        if (nkt == 1) {
+          load_piece(first, 0, &tma_bar[0], smem);
+          if (n_my > 1) load_piece(first + stride, 0, &tma_bar[1], smem + 4 * op_bytes);
+        } else {
+          for (int piece = 0; piece < 3; ++piece) load_piece(first, piece, &tma_bar[piece], smem);
+          if (n_my > 1) prefetch_item(first + stride);
+        }
+        start_item(0);
+      }
+      for (int k = 0; k < n_my; ++k) {
+        const int next_item = first + (k + 1) * stride;
+        int lc = 0;
+        if (nkt == 1) {
+          bind_cur(k & 1);
+          if (chunks == 1 && k + 1 < n_my) {  // the other chunk buffer is free: item k+1 starts before item k is consumed
+            open_next(k + 1);
+            issue_sdp(cc + 1);
           }
-          // the chunk two ahead reuses this chunk's buffer: ordered behind dV above in the MMA pipe, and issued
-          // before the pair's dK/dQ so the elementwise warps do not wait for it
-          if (lc + 2 < chunks) issue_sdp(lc + 2, cc + 2);
-          if ((qc & 1) || qc == nqc - 1) {    // a pair of chunks (<= 128 queries) is complete
-            const int qt = qc >> 1, q0 = qt * 128;
-            const int wp = min(128, NK - q0);
-            const uint32_t tiles = sRing + (pair & 1) * 2 * TILE;
-            {                                 // dK[kt] += dS^T Q[pair]
-              const uint64_t a = desc_at(dk0, tiles);
-              uint64_t b = desc_at(dmn0, sQ + q0 * 128);
-              for (int j = 0; j < (wp >> 4); ++j, b += 128)
-                umma_bf16(tDK, a + (j >> 2) * (TILE >> 4) + (j & 3) * 2, b, idesc_dv, (qt | j) != 0);
+        }
+        for (int kt = 0; kt < nkt; ++kt) {
+          const int ksteps = (kt == 0 ? RA : RB) >> 4;
+          for (int qc = 0; qc < nqc; ++qc, ++lc, ++cc) {
+            const bool last_qc = qc == nqc - 1;
+            const int w16 = last_qc ? w_last >> 4 : 4;                  // 16-query steps in this chunk
+            if (leader) BPROF(1, cc, 0);
+            mbar_wait(&e_done[cc & 1], (cc >> 1) & 1);
+            tc_fence_after();
+            if (leader) BPROF(1, cc, 1);
+            if (qc == 0 && tile_ctr > 0) mbar_wait(acc_free, (tile_ctr - 1) & 1);   // dV/dK of the previous tile read
+            if (leader) BPROF(1, cc, 2);
+            // dV[kt] += P^T dO[chunk]   (A: packed P^T in this chunk's S^T columns, 8 columns per 16 queries)
+            const uint32_t tb = tmem + (cc & 1) * 128;
+            {
+              const uint64_t b = mDO + qc * 512;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (leader && j < w16) umma_bf16_ts(tDV, tb + 16 * j, b + 128 * j, idesc_dv, (qc | j) != 0);
             }
-            if (kt == 0 && qt == 0 && k > 0) mbar_wait(dq_free, (k - 1) & 1);     // dQ of the previous item read
-            const int ksteps = (kt == 0 ? RA : RB) >> 4;
-            {                                 // dQ[pair] += dS K[kt]   (A MN-major: 2 blocks of 64 queries)
-              uint64_t a = desc_at(dq0, tiles), b = desc_at(dmn0, sK + kt * 128 * 128);
-              for (int j = 0; j < ksteps; ++j, a += 128, b += 128)
-                umma_bf16(tDQ + 64 * qt, a, b, idesc_dq, (kt | j) != 0);
+            // the chunk two ahead reuses this chunk's buffer: ordered behind dV above in the MMA pipe, and issued
+            // before the pair's dK/dQ so the elementwise warps do not wait for it
+            if (lc + 2 < chunks) {
+              if (nkt == 2 && lc == 0) {      // chunk 2 is the first to read rows >= 128 (piece 2)
+                mbar_wait(&tma_bar[2], k & 1);
+                tc_fence_after();
+              }
+              issue_sdp(cc + 2);
+            } else if (nkt == 1 && chunks == 2 && k + 1 < n_my) {
+              if (lc == 0) open_next(k + 1);
+              issue_sdp(cc + 2);              // chunk lc of item k+1 into the buffer this chunk has just vacated
             }
-            umma_commit(&pair_done[pair & 1]);
-            ++pair;
+            // two key tiles: parts of the operand set are dead from here on -> the next item's copy of them.  The
+            // pair waited for is the most recently committed one (a parity wait must not fall two phases behind).
+            if (nkt == 2 && kt == 1 && (qc == 0 || qc == 2) && k + 1 < n_my) {
+              mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);
+              const int piece = qc == 0 ? 0 : 1;
+              load_piece(next_item, piece, &tma_bar[piece], smem);
+            }
+            if ((qc & 1) || last_qc) {        // a pair of chunks (<= 128 queries) is complete
+              const int qt = qc >> 1;
+              const int wp16 = last_qc ? wp16_last : 8;
+              const uint32_t tiles = sRing + (pair & 1) * 2 * TILE;
+              {                               // dK[kt] += dS^T Q[pair]
+                const uint64_t a = desc_at(dk0, tiles), b = mQ + qt * 1024;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (leader && j < wp16) umma_bf16(tDK, a + (j >> 2) * (TILE >> 4) + (j & 3) * 2, b + 128 * j, idesc_dv, (qt | j) != 0);
+              }
+              if (kt == 0 && qt == 0 && k > 0) mbar_wait(dq_free, (k - 1) & 1);   // dQ of the previous item read
+              {                               // dQ[pair] += dS K[kt]   (A MN-major: 2 blocks of 64 queries)
+                const uint64_t a = desc_at(dq0, tiles), b = mK + kt * 1024;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (leader && j < ksteps) umma_bf16(tDQ + 64 * qt, a + 128 * j, b + 128 * j, idesc_dq, (kt | j) != 0);
+              }
+              if (leader) umma_commit(&pair_done[pair & 1]);
+              ++pair;
+            }
+            if (last_qc) ++tile_ctr;
+            if (leader) BPROF(1, cc, 3);
           }
-          if (qc == nqc - 1) ++tile_ctr;
+        }
+        if (k + 1 < n_my) {
+          if (nkt == 2) start_item(k + 1);    // queued behind this item's MMAs: no bubble at the item boundary
+          mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);           // every operand of item k is dead
+          if (nkt == 2) {
+            load_piece(next_item, 2, &tma_bar[2], smem);
+            if (k + 2 < n_my) prefetch_item(first + (k + 2) * stride);
+          } else if (k + 2 < n_my) {
+            load_piece(first + (k + 2) * stride, 0, &tma_bar[k & 1], smem + (k & 1) * 4 * op_bytes);
+          }
         }
       }
+    }
+  } else if (warp > kSoftmaxWarps) {
+    // ================= vector warps: lse2[q] = lse[q]*log2(e) and D[q] = <dO[q], O[q]> of every item =================
+    // 64 KB of O / dO rows per item through plain loads: done by warps of their own, an item ahead of the elementwise
+    // warps (double-buffered vectors), so that nobody on the MMA <-> elementwise critical path waits for global memory.
+    // A token's 128-byte head row is read by 8 lanes (16 bytes each): a warp instruction covers 4 whole rows.
+    const int vw = warp - kSoftmaxWarps - 1, sub = lane & 7;
+    const uint32_t vec = smem_u32(vec_base);
+    constexpr int PER = 256 / kVecWarps;      // tokens per vector warp
+    for (int k = 1; k < n_my; ++k) {          // (item 0: by the elementwise warps, which have nothing else to do yet)
+      if (k >= 2) mbar_wait(&vec_free[k & 1], ((k >> 1) - 1) & 1);
+      int cg, b, h;
+      item_bh(first + k * stride, cg, b, h);
+      const __nv_bfloat16* po = G.o[cg] + static_cast<size_t>(b) * N * d + h * HD + sub * 8;
+      const __nv_bfloat16* pg = G.d_o[cg] + static_cast<size_t>(b) * N * d + h * HD + sub * 8;
+      const float* pl = G.lse[cg] + (static_cast<size_t>(b) * H + h) * N;
+      const uint32_t vl = vec + (k & 1) * 2048, vd = vl + 1024;
+#pragma unroll 1
+      for (int t0 = vw * PER; t0 < (vw + 1) * PER; t0 += 32) {     // 32 tokens: 8 loads per array and lane in flight
+        uint4 a[8], g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int tok = t0 + 4 * i + (lane >> 3);
+          a[i] = make_uint4(0u, 0u, 0u, 0u);
+          g[i] = a[i];
+          if (tok < N) {
+            a[i] = *reinterpret_cast<const uint4*>(po + static_cast<size_t>(tok) * d);
+            g[i] = *reinterpret_cast<const uint4*>(pg + static_cast<size_t>(tok) * d);
+          }
+        }
+        const float l2 = t0 + lane < N ? pl[t0 + lane] * 1.4426950408889634f : INFINITY;   // padding: P = exp2(-inf) = 0
+        float dd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t aw[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+          float acc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), acc);
+            acc = fmaf(__uint_as_float(aw[e] & 0xFFFF0000u), __uint_as_float(gw[e] & 0xFFFF0000u), acc);
+          }
+          dd[i] = acc;
+        }
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], m);
+        }
+        if (sub == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_shared_f32(vd + (t0 + 4 * i + (lane >> 3)) * 4, dd[i]);
+        }
+        st_shared_f32(vl + (t0 + lane) * 4, l2);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&vec_full[k & 1]);
     }
   } else {
     // ================= elementwise warps =================
@@ -567,32 +762,6 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t vec = smem_u32(vec_base);
     const float sc = scale * 1.4426950408889634f;
-    // lse2 / D of an item -> vector buffer (item parity); one token per thread (<= 256 < 512 threads)
-    auto compute_vectors = [&](int k) {
-      const int t = threadIdx.x;
-      if (t < 256) {
-        int cg, b, h;
-        item_bh(first + k * stride, cg, b, h);
-        float l2 = INFINITY, dd = 0.f;        // padding queries: P = exp2(-inf) = 0
-        if (t < N) {
-          l2 = G.lse[cg][(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
-          const uint4* po = reinterpret_cast<const uint4*>(G.o[cg] + (static_cast<size_t>(b) * N + t) * d + h * HD);
-          const uint4* pg = reinterpret_cast<const uint4*>(G.d_o[cg] + (static_cast<size_t>(b) * N + t) * d + h * HD);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 a = po[i], g = pg[i];
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              dd = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), dd);
-              dd = fmaf(__uint_as_float(aw[e] & 0xFFFF0000u), __uint_as_float(gw[e] & 0xFFFF0000u), dd);
-            }
-          }
-        }
-        st_shared_f32(vec + (k & 1) * 2048 + t * 4, l2);
-        st_shared_f32(vec + (k & 1) * 2048 + 1024 + t * 4, dd);
-      }
-    };
     // 64 accumulator columns of this thread's row -> 16 per warp group -> bf16 -> 32 bytes of dqkv.
     // The rounded values that were stored are returned in v (0 for rows past the sequence) for the bias gradient.
     auto store_acc = [&](__nv_bfloat16* dqkv, uint32_t tcol, float mul, int tok, int b, int col, float (&v)[16], bool accumulate_v) {
@@ -614,6 +783,27 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
         v[2 * i + 1] = accumulate_v ? v[2 * i + 1] + hi : hi;
       }
     };
+    // staged form: the 32 bytes go into the swizzled staging tile `tile` (row = this thread's accumulator row); one
+    // TMA store per tile then writes 128 rows x 128 bytes.  (Per-thread 32-byte global stores cost the LSU one
+    // request per sector: ~4-6 k cycles per key tile with every elementwise warp — and the tensor pipe — waiting.)
+    auto stage_acc = [&](uint32_t tile, uint32_t tcol, float mul, int tok, float (&v)[16], bool accumulate_v) {
+      float f[16];
+      tmem_ld_32x16(tcol + lane_off + grp * 16, f);
+      tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack2(f[2 * i] * mul, f[2 * i + 1] * mul);
+      const uint32_t rsw = (tile + row * 128) | ((row & 7) << 4);
+      sts_u4(rsw ^ ((2 * grp) << 4), pk[0], pk[1], pk[2], pk[3]);
+      sts_u4(rsw ^ ((2 * grp + 1) << 4), pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float lo = tok < N ? __uint_as_float(pk[i] << 16) : 0.f, hi = tok < N ? __uint_as_float(pk[i] & 0xFFFF0000u) : 0.f;
+        v[2 * i] = accumulate_v ? v[2 * i] + lo : lo;
+        v[2 * i + 1] = accumulate_v ? v[2 * i + 1] + hi : hi;
+      }
+    };
+    auto stage_sync = [&]() { asm volatile("bar.sync 2, 512;" ::: "memory"); };
     // colsum[col + 16*grp + c] += sum over the warp's 32 rows of v[c]: halving butterfly (16 shuffles for the 16
     // columns) and one atomic per column and warp.
     auto add_colsum = [&](float (&v)[16], float* colsum, int col) {
@@ -634,8 +824,50 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
     // last key tile has a spare row (N % 128 != 0) its row 127 of P^T is set to 1 for every real query, so that
     // row of the dV accumulator IS the column sum (fp32, exact) and its 4 threads add it to dbias.
     const bool ones_row = has_dbias && (N & 127) != 0;
-    if (n_my > 0) compute_vectors(0);
-    softmax_warps_sync();
+    if (n_my > 0) {
+      // lse2 / D of the CTA's first item, by all 512 threads in one round trip (the vector warps take items 1, 2, ...)
+      const int t = threadIdx.x, sub = t & 7;
+      int cg, b, h;
+      item_bh(first, cg, b, h);
+      const __nv_bfloat16* po = G.o[cg] + static_cast<size_t>(b) * N * d + h * HD + sub * 8;
+      const __nv_bfloat16* pg = G.d_o[cg] + static_cast<size_t>(b) * N * d + h * HD + sub * 8;
+      uint4 a[4], g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = i * 64 + (t >> 3);
+        a[i] = make_uint4(0u, 0u, 0u, 0u);
+        g[i] = a[i];
+        if (tok < N) {
+          a[i] = *reinterpret_cast<const uint4*>(po + static_cast<size_t>(tok) * d);
+          g[i] = *reinterpret_cast<const uint4*>(pg + static_cast<size_t>(tok) * d);
+        }
+      }
+      float l2 = INFINITY;
+      if (t < N) l2 = G.lse[cg][(static_cast<size_t>(b) * H + h) * N + t] * 1.4426950408889634f;
+      float dd[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t aw[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), acc);
+          acc = fmaf(__uint_as_float(aw[e] & 0xFFFF0000u), __uint_as_float(gw[e] & 0xFFFF0000u), acc);
+        }
+        dd[i] = acc;
+      }
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], m);
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st_shared_f32(vec + 1024 + (i * 64 + (t >> 3)) * 4, dd[i]);
+      }
+      if (t < 256) st_shared_f32(vec + t * 4, l2);
+    }
+    stage_sync();                             // item 0's vectors are visible to every elementwise warp
     int cc = 0, pair = 0;
     int pend_kv = -1, pend_kv_pair = 0, pend_kv_item = 0;   // key tile whose dV/dK still sit in TMEM (-1: none)
     int pend_dq_item = -1, pend_dq_pair = 0;                // item whose dQ still sits in TMEM
@@ -658,14 +890,50 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
             for (int c = 0; c < 16; ++c) atomicAdd(dbias + 2 * d + h * HD + grp * 16 + c, f[c]);
           }
         }
-        store_acc(dqkv, tDV, 1.0f, key, b, 2 * d + h * HD, v, false);
-        if (dbias != nullptr && !ones_row) add_colsum(v, dbias, 2 * d + h * HD);
-        // the K bias gradient is identically zero (softmax is invariant to a shift of the scores): nothing to add
-        store_acc(dqkv, tDK, scale, key, b, d + h * HD, v, false);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_free);
-        pend_kv = -1;
+        if (staged) {
+          if (threadIdx.x == 0) BPROF(0, cc, 8);
+          if (threadIdx.x == 0) tma_store_wait_read();           // the staging tiles' previous stores have been read out
+          if (threadIdx.x == 0) BPROF(0, cc, 9);
+          stage_sync();
+          if (threadIdx.x == 0) BPROF(0, cc, 10);
+          stage_acc(sStage, tDV, 1.0f, key, v, false);
+          if (dbias != nullptr && !ones_row) add_colsum(v, dbias, 2 * d + h * HD);
+          stage_acc(sStage + TILE, tDK, scale, key, v, false);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_free);
+          // an item that is a single chunk (N <= 64) never touches ring tile 1: dQ is staged there and leaves with dV/dK
+          constexpr bool one_shot = ONE_CHUNK;
+          if constexpr (one_shot) {
+            stage_acc(sRing + TILE, tDQ, scale, row, v, false);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+            if (dbias != nullptr) add_colsum(v, dbias, h * HD);
+            pend_dq_item = -1;
+          }
+          if (threadIdx.x == 0) BPROF(0, cc, 11);
+          fence_proxy_async();
+          stage_sync();
+          if (threadIdx.x == 0) BPROF(0, cc, 12);
+          if (threadIdx.x == 0) {
+            tma_store_3d(&G.maps[cg].dqkv_st, stage_ptr, 2 * d + h * HD, pend_kv * 128, b);
+            tma_store_3d(&G.maps[cg].dqkv_st, stage_ptr + TILE, d + h * HD, pend_kv * 128, b);
+            if (one_shot) tma_store_3d(&G.maps[cg].dqkv_st, stage_ptr - (kRing - 1) * TILE, h * HD, 0, b);
+            tma_store_commit();
+          }
+          pend_kv = -1;
+          return;                             // (several chunks: dQ leaves one chunk later, when these stores have drained)
+        } else {
+          store_acc(dqkv, tDV, 1.0f, key, b, 2 * d + h * HD, v, false);
+          if (dbias != nullptr && !ones_row) add_colsum(v, dbias, 2 * d + h * HD);
+          // the K bias gradient is identically zero (softmax is invariant to a shift of the scores): nothing to add
+          store_acc(dqkv, tDK, scale, key, b, d + h * HD, v, false);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_free);
+          pend_kv = -1;
+        }
       }
       if (pend_dq_item >= 0) {
         mbar_wait(&pair_done[pend_dq_pair & 1], (pend_dq_pair >> 1) & 1);
@@ -674,30 +942,50 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
         item_bh(pend_dq_item, cg, b, h);
         float* dbias = G.dbias[cg];
         float v[16];                          // both query tiles summed per thread: one reduction per item
-        for (int qt = 0; qt < nkt; ++qt) store_acc(G.dqkv[cg], tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, v, qt > 0);
-        if (dbias != nullptr) add_colsum(v, dbias, h * HD);
+        if (staged) {
+          if (threadIdx.x == 0) tma_store_wait_read();
+          stage_sync();
+          for (int qt = 0; qt < nkt; ++qt) stage_acc(sStage + qt * TILE, tDQ + 64 * qt, scale, qt * 128 + row, v, qt > 0);
+        } else {
+          for (int qt = 0; qt < nkt; ++qt) store_acc(G.dqkv[cg], tDQ + 64 * qt, scale, qt * 128 + row, b, h * HD, v, qt > 0);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_free);
+        if (dbias != nullptr) add_colsum(v, dbias, h * HD);
+        if (staged) {
+          fence_proxy_async();
+          stage_sync();
+          if (threadIdx.x == 0) {
+            for (int qt = 0; qt < nkt; ++qt) tma_store_3d(&G.maps[cg].dqkv_st, stage_ptr + qt * TILE, h * HD, qt * 128, b);
+            tma_store_commit();
+          }
+        }
         pend_dq_item = -1;
       }
     };
     for (int k = 0; k < n_my; ++k) {
       const int item = first + k * stride;
       const uint32_t vl = vec + (k & 1) * 2048, vd = vl + 1024;
+      // this item's lse2 / D (written by the vector warps, an item ahead); buffer 0's first fill is item 0, above
+      if (k > 0) mbar_wait(&vec_full[k & 1], (k & 1) ? (k >> 1) & 1 : ((k >> 1) - 1) & 1);
       for (int kt = 0; kt < nkt; ++kt) {
         for (int qc = 0; qc < nqc; ++qc, ++cc) {
           const int W = min(64, NK - 64 * qc);
           const uint32_t tb = tmem + (cc & 1) * 128 + lane_off;
           // ring tile of this chunk; its previous user (pair - 2) must have been consumed by dK/dQ
+          if (threadIdx.x == 0) BPROF(0, cc, 0);
           if ((qc & 1) == 0 && pair >= 2) mbar_wait(&pair_done[pair & 1], ((pair >> 1) - 1) & 1);
+          if (threadIdx.x == 0) BPROF(0, cc, 1);
           mbar_wait(&sdp_full[cc & 1], (cc >> 1) & 1);
           tc_fence_after();
+          if (threadIdx.x == 0) BPROF(0, cc, 2);
           if (16 * grp < W) {                 // warp-uniform
             float s[16], dp[16];
             tmem_ld_32x16(tb + 16 * grp, s);
             tmem_ld_32x16(tb + 64 + 16 * grp, dp);
             tmem_ld_wait();
+            if (threadIdx.x == 0) BPROF(0, cc, 3);
             const int q0 = 64 * qc + 16 * grp;
             uint32_t pp[8], ds[8];
 #pragma unroll
@@ -728,10 +1016,13 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
             tmem_st_wait();
             fence_proxy_async();
           }
+          if (threadIdx.x == 0) BPROF(0, cc, 4);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&e_done[cc & 1]);
+          if (threadIdx.x == 0) BPROF(0, cc, 5);
           flush_pending();                    // outputs of the previous key tile / item, now that this chunk is handed over
+          if (threadIdx.x == 0) BPROF(0, cc, 6);
           if ((qc & 1) || qc == nqc - 1) {
             if (qc == nqc - 1) {
               pend_kv = kt;
@@ -744,14 +1035,15 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
             }
             ++pair;
           }
-          if (kt == 0 && qc == 0 && k + 1 < n_my) {   // next item's vectors, one item ahead
-            compute_vectors(k + 1);
-          }
+          if (threadIdx.x == 0) BPROF(0, cc, 7);
         }
       }
-      softmax_warps_sync();                   // next item's vectors are visible to every warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&vec_free[k & 1]);
     }
     flush_pending();
+    flush_pending();                          // (staged: dQ leaves in a second step)
+    if (staged && threadIdx.x == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -865,6 +1157,7 @@ extern "C" int fc_attention_bwd_grouped(int groups, const void* const* qkv, cons
     if (!rc) rc = make_tmap3(&m.qkv_b, qkv[g], B, N, 3 * H * HD, RB ? RB : RA);
     if (!rc) rc = make_tmap3(&m.do_a, d_out[g], B, N, H * HD, RA);
     if (!rc) rc = make_tmap3(&m.do_b, d_out[g], B, N, H * HD, RB ? RB : RA);
+    if (!rc) rc = make_tmap3(&m.dqkv_st, dqkv[g], B, N, 3 * H * HD, RA);
     if (rc) return rc;
     G.o[g] = static_cast<const __nv_bfloat16*>(out[g]);
     G.d_o[g] = static_cast<const __nv_bfloat16*>(d_out[g]);
@@ -872,13 +1165,20 @@ extern "C" int fc_attention_bwd_grouped(int groups, const void* const* qkv, cons
     G.dqkv[g] = static_cast<__nv_bfloat16*>(dqkv[g]);
     G.dbias[g] = dbias ? dbias[g] : nullptr;
   }
-  const int smem = 4 * NK * 128 + kRing * TILE + 4096 + 128;
-  FC_SMEM_OPT_IN(attn_bwd_tc_kernel, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
+  int smem = (RB ? 1 : 2) * 4 * NK * 128 + kRing * TILE + 4096 + 256;            // two operand sets for one key tile
+  // gradients leave through two staging tiles + TMA stores when they fit
+  const int staged = smem + 2 * TILE <= kMaxDynSmem ? 2 : 0;
+  smem += staged * TILE;
+  FC_SMEM_OPT_IN(attn_bwd_tc_kernel<false>, kMaxDynSmem);   // one process-wide value: the attribute is per function, not per thread
+  FC_SMEM_OPT_IN(attn_bwd_tc_kernel<true>, kMaxDynSmem);
   const int items = groups * B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
   const int grid = fc_apply_grid_cap((items + waves - 1) / waves);
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, 0.125f);
+  if (NK <= 64 && staged)
+    attn_bwd_tc_kernel<true><<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, 0.125f, staged);
+  else
+    attn_bwd_tc_kernel<false><<<grid, kBwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, 0.125f, staged);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
