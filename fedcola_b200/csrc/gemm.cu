@@ -574,8 +574,12 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run their loops warp-uniform; only the TMA / MMA / commit / arrive instructions are
+  // predicated on the elected lane.  (Inside an `if (lane == 0)` branch the compiler cannot keep descriptors in
+  // uniform registers and wraps every UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop: tools/mma_probe.cu.)
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
       for (int tile = walk.first; tile < walk.total; tile += walk.step) {
@@ -597,33 +601,33 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
             // (The peer's bytes may land before the leader arms the phase: the transaction count just goes negative;
             //  they cannot run a phase ahead, because the peer's slot is only freed by the commit of this phase's MMAs.)
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
-            if (walk.rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            if (walk.rank == 0 && leader) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
             if (A_MN) {
-              tma_load_2d_pair(a_dst, tmA, lbar, m0, kb * BK);
-              tma_load_2d_pair(a_dst + 8192, tmA, lbar, m0 + 64, kb * BK);
+              if (leader) tma_load_2d_pair(a_dst, tmA, lbar, m0, kb * BK);
+              if (leader) tma_load_2d_pair(a_dst + 8192, tmA, lbar, m0 + 64, kb * BK);
             } else {
-              tma_load_2d_pair(a_dst, tmA, lbar, kb * BK, m0);
+              if (leader) tma_load_2d_pair(a_dst, tmA, lbar, kb * BK, m0);
             }
             const int nh = n0 + walk.rank * (BN / 2);          // this CTA's half of the B tile
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(b_dst + j * 8192, tmB, lbar, nh + j * 64, kb * BK);
+              for (int j = 0; j < BN / 128; ++j) if (leader) tma_load_2d_pair(b_dst + j * 8192, tmB, lbar, nh + j * 64, kb * BK);
             } else {      // box {64 (k), BN/2 (n)}
-              tma_load_2d_pair(b_dst, tmB, lbar, kb * BK, nh);
+              if (leader) tma_load_2d_pair(b_dst, tmB, lbar, kb * BK, nh);
             }
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
             if (A_MN) {   // [K, M] global: boxes {64 (m), 64 (k)}
-              tma_load_2d(a_dst, tmA, &full_bar[s], m0, kb * BK);
-              tma_load_2d(a_dst + 8192, tmA, &full_bar[s], m0 + 64, kb * BK);
+              if (leader) tma_load_2d(a_dst, tmA, &full_bar[s], m0, kb * BK);
+              if (leader) tma_load_2d(a_dst + 8192, tmA, &full_bar[s], m0 + 64, kb * BK);
             } else {      // [M, K] global: box {64 (k), 128 (m)}
-              tma_load_2d(a_dst, tmA, &full_bar[s], kb * BK, m0);
+              if (leader) tma_load_2d(a_dst, tmA, &full_bar[s], kb * BK, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, tmB, &full_bar[s], n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) if (leader) tma_load_2d(b_dst + j * 8192, tmB, &full_bar[s], n0 + j * 64, kb * BK);
             } else {      // box {64 (k), BN (n)}
-              tma_load_2d(b_dst, tmB, &full_bar[s], kb * BK, n0);
+              if (leader) tma_load_2d(b_dst, tmB, &full_bar[s], kb * BK, n0);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -632,7 +636,8 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !(pair && walk.rank != 0)) {     // pair mode: the leader issues for both CTAs
+    if (!(pair && walk.rank != 0)) {     // pair mode: the leader CTA issues for both
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(pair ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
@@ -645,7 +650,7 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_COLS;
         if ((p.debug & 2) && !pair) {          // measurement aid: no operands, no MMAs — epilogue-only timing
-          mbar_arrive(&tmem_full_bar[buf]);
+          if (leader) mbar_arrive(&tmem_full_bar[buf]);
           continue;
         }
         uint32_t acc_flag = 0;                 // 0 for the very first MMA of the tile, 1 afterwards
@@ -662,16 +667,22 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
                                      : umma_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            if constexpr (pair) umma_bf16_pair(d_tmem, ad, bd, idesc, acc_flag);
-            else umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+            if (leader) {
+              if constexpr (pair) umma_bf16_pair(d_tmem, ad, bd, idesc, acc_flag);
+              else umma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+            }
             acc_flag = 1u;
           }
-          if constexpr (pair) umma_commit_pair(&empty_bar[s]);   // slot free in both CTAs once these MMAs retire
-          else umma_commit(&empty_bar[s]);     // smem slot free once these MMAs retire
+          if (leader) {
+            if constexpr (pair) umma_commit_pair(&empty_bar[s]);   // slot free in both CTAs once these MMAs retire
+            else umma_commit(&empty_bar[s]);     // smem slot free once these MMAs retire
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if constexpr (pair) umma_commit_pair(&tmem_full_bar[buf]);   // accumulator halves complete in both CTAs
-        else umma_commit(&tmem_full_bar[buf]); // accumulator complete
+        if (leader) {
+          if constexpr (pair) umma_commit_pair(&tmem_full_bar[buf]);   // accumulator halves complete in both CTAs
+          else umma_commit(&tmem_full_bar[buf]); // accumulator complete
+        }
       }
     }
   } else {
