@@ -161,11 +161,13 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
   const int n_my = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
   if (warp == kSoftmaxWarps) {
-    // ================= control warp: TMA producer + MMA issuer (one lane) =================
-    if (lane == 0 && n_my > 0) {
+    // ================= control warp: TMA producer + MMA issuer =================
+    // warp-uniform control flow, elect-predicated TMA / MMA / commit (see the backward's control warp)
+    if (n_my > 0) {
+      const bool leader = elect_one();
       for (int g = 0; g * items_per_group < n_items; ++g) {
-        prefetch_tmap(&G.maps[g].qkv_a);
-        prefetch_tmap(&G.maps[g].qkv_b);
+        if (leader) prefetch_tmap(&G.maps[g].qkv_a);
+        if (leader) prefetch_tmap(&G.maps[g].qkv_b);
       }
       const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
@@ -177,10 +179,10 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
         const FwdMaps& maps = G.maps[grp];
         uint8_t* base = smem + (k % nbuf) * buf_bytes;
         uint64_t* bar = &tma_bar[k % nbuf];
-        mbar_arrive_expect_tx(bar, buf_bytes);
+        if (leader) mbar_arrive_expect_tx(bar, buf_bytes);
         for (int op = 0; op < 3; ++op) {      // Q, K, V column blocks of this head
-          tma_load_3d(base + op * op_bytes, &maps.qkv_a, bar, op * d + h * HD, 0, b);
-          if (RB) tma_load_3d(base + op * op_bytes + RA * 128, &maps.qkv_b, bar, op * d + h * HD, 128, b);
+          if (leader) tma_load_3d(base + op * op_bytes, &maps.qkv_a, bar, op * d + h * HD, 0, b);
+          if (RB && leader) tma_load_3d(base + op * op_bytes + RA * 128, &maps.qkv_b, bar, op * d + h * HD, 128, b);
         }
       };
       const uint64_t dk0 = desc_k(0), dmn0 = desc_mn(0);
@@ -190,8 +192,8 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
         const uint64_t q = desc_at(dk0, buf_addr(k) + qt * TILE), kk = desc_at(dk0, buf_addr(k) + op_bytes);
         const uint32_t ts = tmem + sbuf * s_stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(ts, q + 2 * j, kk + 2 * j, idesc_s, j > 0);   // 32 bytes per k-step
-        umma_commit(&s_full[sbuf]);
+        for (int j = 0; j < 4; ++j) if (leader) umma_bf16(ts, q + 2 * j, kk + 2 * j, idesc_s, j > 0);   // 32 bytes per k-step
+        if (leader) umma_commit(&s_full[sbuf]);
       };
       // Issue order is a small state machine: loads run up to nbuf items ahead (a buffer is reusable once the last
       // P·V of its item completed), QK^T runs up to `depth` tiles ahead of the softmax (an S buffer is reusable
@@ -216,8 +218,8 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
         // 8*(ks&1) — each softmax warp packed its 32-score slabs in place (slab at +32*half, packed into its first 16)
         const uint32_t tP = tmem + (depth == 2 ? (T & 1) : 0) * s_stride;
         for (int ks = 0; ks < ksteps; ++ks, vv += 128)     // 16 key rows of V = 2048 bytes
-          umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), vv, idesc_o, ks > 0);
-        umma_commit(o_full);
+          if (leader) umma_bf16_ts(tmem + o_col, tP + 64 * (ks >> 2) + 32 * ((ks >> 1) & 1) + 8 * (ks & 1), vv, idesc_o, ks > 0);
+        if (leader) umma_commit(o_full);
         pump(T + 1);
         if ((T + 1) % q_tiles == 0) {
           mbar_wait(o_full, T & 1);           // every MMA reading buffer k % nbuf has completed

@@ -399,13 +399,15 @@ template <bool REDUCE>
 __device__ __forceinline__ void stage_store(const CUtensorMap* map, const void* buf_ptr, int col0, int row0, int lane) {
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) {
+  // elect.sync picks the same lane for the same (full) mask every time: the bulk-group wait in stage_acquire() is
+  // executed by the thread that committed the store.  (`lane == 0` would put the UTMASTG in a BRA.U.ANY loop.)
+  if (elect_one()) {
     if (REDUCE) tma_reduce_add_2d(map, buf_ptr, col0, row0); else tma_store_2d(map, buf_ptr, col0, row0);
     tma_store_commit();
   }
 }
 __device__ __forceinline__ void stage_acquire(int lane) {
-  if (lane == 0) tma_store_wait_read();     // previous store of this warp has finished reading the buffer
+  if (elect_one()) tma_store_wait_read();   // previous store of this warp has finished reading the buffer
   __syncwarp();
 }
 
@@ -764,7 +766,7 @@ gemm_bf16_kernel(const __grid_constant__ AllMaps maps, const __grid_constant__ G
           __syncwarp();
         } else {
           if constexpr (EpiTraits<EPI>::kLoads) {     // fused operand tile (residual / saved gelu') -> staging buffer
-            if (lane == 0) {
+            if (elect_one()) {                 // (the same lane as in stage_store / stage_acquire)
               tma_store_wait_read();           // the previous store out of this buffer has drained
               mbar_arrive_expect_tx(ebar, EPI_BUF_BYTES);
               tma_load_2d(buf_ptr, tmR, ebar, col0, row0);
