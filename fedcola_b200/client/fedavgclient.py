@@ -108,6 +108,9 @@ class _ClientData:
         bmax = max(len(b) for b in batches)
         probe = self.cols if self.cols is not None else self._collate(batches[0][:1])
         slots = [[torch.empty((bmax,) + tuple(c.shape[1:]), dtype=c.dtype, device=dev) for c in probe] for _ in range(2)]
+        # the allocator may hand out blocks whose previous users (kernels already enqueued on the compute stream) have
+        # not run yet — safe for work on that stream, not for the copies of the side stream
+        side.wait_stream(compute)
         free_ev, ready_ev, keep = [None, None], [None, None], [None, None]
 
         def issue(k):
