@@ -102,6 +102,7 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t zero_addr_desc, uint32_t ad
 constexpr int MAXG = FC_ATTN_MAX_GROUPS;
 struct FwdMaps {
   CUtensorMap qkv_a, qkv_b;                  // box rows RA (first 128-token tile) / RB (remainder tile)
+  CUtensorMap out_st;                        // output store: box = 64 columns x RA rows (rows past N are clipped)
 };
 struct FwdGroups {
   FwdMaps maps[MAXG];
@@ -113,9 +114,11 @@ struct FwdGroups {
 // the next items' Q/K/V by TMA (nbuf smem buffers) and issues every tcgen05.mma; warps 0-15 do the softmax and the
 // output.  S accumulators are double-buffered in TMEM (columns 0 / 256) and O overlays its own consumed S, so
 // QK^T of tile T+1 and P·V of tile T run under the softmax warps' work on the neighbouring tiles.
-__global__ void __launch_bounds__(kFwdThreads, 1)
+template <bool STAGED>                       // STAGED: O leaves through staging tiles + TMA stores (own code, own registers)
+__global__ void __launch_bounds__(kFwdThreads, 1)   // 17 warps = 5 on one SM sub-partition: 96 registers per thread at most
 attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_per_group, int N, int H, int nbuf,
                    float scale_log2e) {
+  constexpr bool staged = STAGED;
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzled tiles need 1024-byte alignment (checked below)
 #ifdef FC_ATTN_PROF
   __shared__ long long prof_s[16 * 12];
@@ -129,7 +132,9 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
   const int buf_bytes = 3 * op_bytes;
   // reduction scratch, double-buffered by tile parity: row-sum partials float [2][4][128], then row-max partials
   // bf16 [2][4][128] (softmax is shift-invariant: a rounded max only has to be the SAME for the whole row)
-  uint8_t* red_base = smem + nbuf * buf_bytes;
+  // staged: two tiles between the operand buffers and the scratch, through which O leaves as TMA stores
+  uint8_t* stage_ptr = smem + nbuf * buf_bytes;
+  uint8_t* red_base = stage_ptr + (staged ? 2 * TILE : 0);
   uint64_t* tma_bar = reinterpret_cast<uint64_t*>(red_base + 6144);    // [4] item operands landed
   uint64_t* s_full = tma_bar + 4;                                      // [2] S buffer written by the tensor core
   uint64_t* o_full = s_full + 2;                                       //     O written (and P, V no longer read)
@@ -259,6 +264,20 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = pack2(f[2 * i] * inv, f[2 * i + 1] * inv);
     };
+    // staged output: the thread's 32 bytes go into the swizzled staging tile of the tile's parity; thread 0 hands the
+    // tile to the TMA engine after the next all-warp barrier (per-thread 32-byte global stores cost the LSU one
+    // request per sector: ~2 k cycles per tile with every softmax warp waiting)
+    const uint32_t sStage = smem_u32(stage_ptr);
+    auto stage_o = [&](const uint32_t (&o)[8], int T_of) {
+      const uint32_t rsw = (sStage + (T_of & 1) * TILE + row * 128) | ((row & 7) << 4);
+      sts_u4(rsw ^ ((2 * grp) << 4), o[0], o[1], o[2], o[3]);
+      sts_u4(rsw ^ ((2 * grp + 1) << 4), o[4], o[5], o[6], o[7]);
+      fence_proxy_async();
+    };
+    auto issue_store = [&](int T_of, int b, int h, int qt, int cg) {      // one thread
+      tma_store_3d(&G.maps[cg].out_st, stage_ptr + (T_of & 1) * TILE, h * HD, qt * 128, b);
+      tma_store_commit();
+    };
     auto store_o = [&](const uint32_t (&o)[8], int bh_row0, int h, int qt, int cg) {
       const int qrow = qt * 128 + row;
       if (qrow < N) {
@@ -283,7 +302,8 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
         lse_out[static_cast<size_t>(bh) * N + qrow] = 0.69314718056f * (mb + lg2(sum));
       return rcp(sum);
     };
-    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0, prev_cg = 0;
+    int T = 0, prev_row0 = 0, prev_h = 0, prev_qt = 0, prev_bh = 0, prev_cg = 0, prev_b = 0;
+    int prev2_b = 0, prev2_h = 0, prev2_qt = 0, prev2_cg = 0;         // tile T-2: its O is staged, not yet handed over
     float prev_mb = 0.f;
     const unsigned long long h_magic = ((1ull << 32) + H - 1) / H;   // item / H == (item * magic) >> 32 for item < 2^16
     for (int k = 0, item = first; k < n_my; ++k, item += stride) {
@@ -315,7 +335,9 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
           }
         }
         st_shared_bf16(red_max + par, fmaxf(m0, m1));
+        if (staged && threadIdx.x == 0) tma_store_wait_read();       // the staging tile written below is free again
         softmax_warps_sync();                 // also: every warp has published the previous tile's row sums
+        if (staged && T >= 2 && threadIdx.x == 0) issue_store(T - 2, prev2_b, prev2_h, prev2_qt, prev2_cg);
         PROF(3);
         const float mx = fmaxf(fmaxf(ld_shared_bf16(red_max_rd + par), ld_shared_bf16(red_max_rd + par + 256)),
                                fmaxf(ld_shared_bf16(red_max_rd + par + 512), ld_shared_bf16(red_max_rd + par + 768)));
@@ -358,7 +380,15 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
         PROF(5);
-        if (T > 0) store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
+        if (T > 0) {
+          if (staged) stage_o(o, T - 1);
+          else store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
+        }
+        prev2_b = prev_b;
+        prev2_h = prev_h;
+        prev2_qt = prev_qt;
+        prev2_cg = prev_cg;
+        prev_b = b;
         prev_mb = mb;
         prev_row0 = b * N;
         prev_bh = rem;
@@ -369,10 +399,21 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
       }
     }
     if (T > 0) {
+      if (staged && threadIdx.x == 0) tma_store_wait_read();
       softmax_warps_sync();                   // last tile's row sums
+      if (staged && T >= 2 && threadIdx.x == 0) issue_store(T - 2, prev2_b, prev2_h, prev2_qt, prev2_cg);
       uint32_t o[8];
       load_o(T - 1, finish_sums(T - 1, prev_mb, prev_bh, prev_qt, prev_cg), o);
-      store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
+      if (staged) {
+        stage_o(o, T - 1);
+        softmax_warps_sync();
+        if (threadIdx.x == 0) {
+          issue_store(T - 1, prev_b, prev_h, prev_qt, prev_cg);
+          tma_store_wait_all();
+        }
+      } else {
+        store_o(o, prev_row0, prev_h, prev_qt, prev_cg);
+      }
     }
   }
   tc_fence_before();
@@ -419,7 +460,7 @@ struct BwdGroups {
 };
 
 template <bool ONE_CHUNK>                   // ONE_CHUNK: N <= 64, an item is a single chunk (own flush path, own code)
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)   // (19 warps: 96 registers is what the file grants in units of 512 per warp)
 attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_per_group, int N, int H, float scale,
                    int staged) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1105,11 +1146,15 @@ extern "C" int fc_attention_fwd_grouped(int groups, const void* const* qkv, void
                "fc_attention_fwd: qkv/out must be 16-byte aligned");
     int rc = make_tmap3(&G.maps[g].qkv_a, qkv[g], B, N, 3 * H * HD, RA);
     if (!rc) rc = make_tmap3(&G.maps[g].qkv_b, qkv[g], B, N, 3 * H * HD, RB ? RB : RA);
+    if (!rc) rc = make_tmap3(&G.maps[g].out_st, out[g], B, N, H * HD, RA);
     if (rc) return rc;
     G.out[g] = static_cast<__nv_bfloat16*>(out[g]);
     G.lse[g] = lse ? lse[g] : nullptr;
   }
-  const int buf_bytes = 3 * NK * 128, aux = 6144 + 128;
+  const int buf_bytes = 3 * NK * 128;
+  // O leaves through two staging tiles + TMA stores when two operand buffers still fit beside them
+  const int staged = 2 * buf_bytes + 6144 + 128 + 2 * TILE <= kMaxDynSmem;
+  const int aux = 6144 + 128 + (staged ? 2 * TILE : 0);
   int nbuf = 4;                                                  // operand buffers: as many as fit (<= 4)
   while (nbuf > 1 && nbuf * buf_bytes + aux > kMaxDynSmem) --nbuf;
   // QK^T is issued with M = 128 whatever N is: the tensor core reads 128 rows (16 KB) from the Q tile's address.  Rows
@@ -1117,14 +1162,17 @@ extern "C" int fc_attention_fwd_grouped(int groups, const void* const* qkv, void
   // the read from the LAST buffer would run past the CTA's shared-memory allocation -> pad the allocation.
   const int pad = buf_bytes < TILE ? TILE - buf_bytes : 0;
   const int smem = nbuf * buf_bytes + aux + pad;
-  FC_SMEM_OPT_IN(attn_fwd_tc_kernel, kMaxDynSmem);
+  FC_SMEM_OPT_IN(attn_fwd_tc_kernel<true>, kMaxDynSmem);
+  FC_SMEM_OPT_IN(attn_fwd_tc_kernel<false>, kMaxDynSmem);
   const int items = groups * B * H;
   const int sms = fc_num_sms(device);
   const int waves = (items + sms - 1) / sms;
   const int grid = fc_apply_grid_cap((items + waves - 1) / waves);   // balanced persistent grid (<= #SMs)
   const float scale_log2e = 0.125f * 1.4426950408889634f;        // 64^-0.5 * log2(e)
-  attn_fwd_tc_kernel<<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, nbuf,
-                                                                                          scale_log2e);
+  if (staged)
+    attn_fwd_tc_kernel<true><<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, nbuf, scale_log2e);
+  else
+    attn_fwd_tc_kernel<false><<<grid, kFwdThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(G, items, B * H, N, H, nbuf, scale_log2e);
   FC_LAUNCH_CHECK();
   return FC_OK;
 }
