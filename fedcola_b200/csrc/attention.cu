@@ -701,6 +701,9 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
             }
             // two key tiles: parts of the operand set are dead from here on -> the next item's copy of them.  The
             // pair waited for is the most recently committed one (a parity wait must not fall two phases behind).
+            // L2 prefetch of the item after next: early in the item, away from the item boundary where the gradient
+            // stores and the piece loads queue up in the TMA unit
+            if (nkt == 2 && lc == 2 && k + 2 < n_my) prefetch_item(first + (k + 2) * stride);
             if (nkt == 2 && kt == 1 && (qc == 0 || qc == 2) && k + 1 < n_my) {
               mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);
               const int piece = qc == 0 ? 0 : 1;
@@ -735,7 +738,6 @@ attn_bwd_tc_kernel(const __grid_constant__ BwdGroups G, int n_items, int items_p
           mbar_wait(&pair_done[(pair - 1) & 1], ((pair - 1) >> 1) & 1);           // every operand of item k is dead
           if (nkt == 2) {
             load_piece(next_item, 2, &tma_bar[2], smem);
-            if (k + 2 < n_my) prefetch_item(first + (k + 2) * stride);
           } else if (k + 2 < n_my) {
             load_piece(first + (k + 2) * stride, 0, &tma_bar[k & 1], smem + (k & 1) * 4 * op_bytes);
           }

@@ -122,6 +122,7 @@ class ModalityAgnosticTransformer(nn.Module):
         # registration order must follow the reference: embeddings, blockses, norm, heads
         self._modules = {k: self._modules[k] for k in ("embeddings", "blockses", "norm", "heads")}
         self._params_by_key = made
+        self.__dict__["_train_synced"] = False
 
     def _apply(self, fn, recurse=True):
         new = fn(self._arena)
@@ -138,7 +139,7 @@ class ModalityAgnosticTransformer(nn.Module):
         new = ModalityAgnosticTransformer.__new__(ModalityAgnosticTransformer)
         nn.Module.__init__(new)
         for k, v in self.__dict__.items():
-            if k in ("_parameters", "_buffers", "_modules", "_arena", "_runtime", "_params_by_key", "_shell_pool") or \
+            if k in ("_parameters", "_buffers", "_modules", "_arena", "_runtime", "_params_by_key", "_shell_pool", "_train_synced") or \
                     k.startswith("_forward") or k.startswith("_backward") or k.startswith("_state_dict") or \
                     k.startswith("_load_state_dict"):
                 continue
@@ -151,6 +152,15 @@ class ModalityAgnosticTransformer(nn.Module):
             new._params_by_key[k].requires_grad_(p.requires_grad)
         new.training = self.training
         return new
+
+    def train(self, mode=True):
+        """nn.Module.train, without walking the ~300 placeholder sub-modules when nothing changes (a round calls this
+        on every client model; the recursion costs ~2 ms of interpreter time per call)."""
+        if self.training == bool(mode) and getattr(self, "_train_synced", False):
+            return self
+        super().train(mode)
+        self.__dict__["_train_synced"] = True
+        return self
 
     def refill_from(self, other):
         """Make this model a copy of `other` (same spec) without rebuilding the module tree: one arena copy (device to
