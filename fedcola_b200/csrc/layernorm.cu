@@ -421,7 +421,7 @@ extern "C" int fc_layernorm_fwd_grouped(int groups, const float* const* x, long 
   }
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
-  const int cap = (fc_num_sms(device) * 8 + groups - 1) / groups;
+  const int cap = (fc_num_sms(device) * 8) / groups;      // rounded down: no CTA of a second wave
   if (grid > cap) grid = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define FC_LN_FWD(NV) ln_fwd_kernel<NV><<<dim3(grid, groups), wpb * 32, 0, st>>>(S, x_row_stride, eps, rows, d)
@@ -488,7 +488,9 @@ extern "C" int fc_layernorm_bwd_grouped(int groups, const void* const* dy, int d
       if (stages >= 2 && stages * stage_bytes >= part_bytes) {
         const int smem_ring = stages * stage_bytes + 2 * stages * 8 + 64;
         const int n_chunks = (rows + kRingRows - 1) / kRingRows;
-        int gx = (fc_num_sms(device) * ctas_per_sm + groups - 1) / groups;   // resident CTAs over all groups
+        // resident CTAs, shared out over the groups — rounded DOWN: one CTA too many would wait for a slot and run as a
+        // second wave of a persistent kernel
+        int gx = (fc_num_sms(device) * ctas_per_sm) / groups;
         if (gx < 1) gx = 1;
         if (gx > n_chunks) gx = n_chunks;
         const int rpg_ = rows_per_group > 0 ? rows_per_group : 1;
@@ -516,7 +518,7 @@ extern "C" int fc_layernorm_bwd_grouped(int groups, const void* const* dy, int d
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
   // 2 resident CTAs/SM (111 registers); measured best of {1,2,3,4,8} per SM — also halves the per-CTA column atomics
-  const int cap = (fc_num_sms(device) * 2 + groups - 1) / groups;
+  const int cap = (fc_num_sms(device) * 2) / groups;      // rounded down: no CTA of a second wave
   if (grid > cap) grid = cap;
   const size_t smem = (at(dgamma, 0) || at(dxs_colsum, 0)) ? sizeof(float) * 3 * wpb * d : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
