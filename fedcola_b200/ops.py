@@ -142,6 +142,21 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dxs=None, row_scale=
     return dx
 
 
+def layernorm_bwd_grouped(dys, xs, means, rstds, gammas, dxs_out, accumulate, dxs=None, row_scales=None, rows_per_group=0,
+                          dgammas=None, dbetas=None, dxs_colsums=None):
+    """The same LayerNorm backward for len(xs) operand sets of one shape in ONE launch (fc_layernorm_bwd_grouped)."""
+    rows, d = xs[0].shape
+    dy, x, dx = dys[0], xs[0], dxs_out[0]
+    rc = _lib.lib().fc_layernorm_bwd_grouped(
+        c_int(len(xs)), _ptr_table(dys), c_int(int(dy.dtype == torch.bfloat16)), c_ll(dy.stride(0)), _ptr_table(xs),
+        c_ll(x.stride(0)), _ptr_table(means), _ptr_table(rstds), _ptr_table(gammas), _ptr_table(dxs_out), c_ll(dx.stride(0)),
+        c_int(int(accumulate)), _ptr_table(dxs), c_ll(dxs[0].stride(0) if dxs is not None else d), _ptr_table(row_scales),
+        c_int(rows_per_group), _ptr_table(dgammas), _ptr_table(dbetas), _ptr_table(dxs_colsums), c_int(rows), c_int(d),
+        c_int(_dev(x)), _st(x))
+    _lib.check(rc, "fc_layernorm_bwd_grouped")
+    return dxs_out
+
+
 # ---- fp32-accurate validation mode (csrc/precise.cu, fc_gemm_split) ------------------------------------
 def split_bf16(x, row_scale=None, rows_per_group=0):
     """fp32 tensor -> (hi, lo) bf16 pair with x ~= hi + lo (16 mantissa bits)."""

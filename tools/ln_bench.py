@@ -29,6 +29,14 @@ def main():
         by_b = rows * d * (2 + 4 + 4 + 4 + 2)
         print(f"rows={rows}: ln_fwd {t_f:6.1f} us ({by_f / t_f / 1e3:5.0f} GB/s)   ln_bwd {t_b:6.1f} us ({by_b / t_b / 1e3:5.0f} GB/s)",
               flush=True)
+        # three clients per launch (a lockstep group): sets i, i+1, i+2 of the rotation
+        G = 3
+        gs, dgs, dbs, css = [g] * G, [dg] * G, [db] * G, [cs] * G
+        t_g = time_graph(lambda i: ops.layernorm_bwd_grouped(
+            [dy[(i + j) % sets] for j in range(G)], [x[(i + j) % sets] for j in range(G)], [mean] * G, [rstd] * G, gs,
+            [dx[(i + j) % sets] for j in range(G)], True, dxs=[dxs[(i + j) % sets] for j in range(G)], row_scales=[scale] * G,
+            rows_per_group=rows // 112, dgammas=dgs, dbetas=dbs, dxs_colsums=css), sets)
+        print(f"rows=3x{rows} (grouped launch): ln_bwd {t_g:6.1f} us ({G * by_b / t_g / 1e3:5.0f} GB/s)", flush=True)
 
 
 if __name__ == "__main__":
