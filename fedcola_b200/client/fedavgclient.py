@@ -145,7 +145,7 @@ class _ClientData:
 LOSS_KIND = {"img": R.LOSS_CE_IMG, "txt": R.LOSS_CE_TXT, "img+txt": R.LOSS_CONTRASTIVE}
 
 
-def update_group(clients):
+def update_group(clients, ready=None):
     """Local training of a LOCKSTEP GROUP of clients: `FedavgClient.update()` (fedavgclient.py:55-116) for every client
     of the group, with batch s of all of them trained by ONE native call (runtime.group_step -> fc_client_step_group:
     every GEMM / attention / LayerNorm launch covers the whole group).  The reference trains the same clients side by
@@ -154,7 +154,10 @@ def update_group(clients):
 
     The clients must sit on one device and hold the same model architecture (the server groups them by dataset);
     batch counts and sizes may differ (a client with fewer batches drops out of the later steps; a short last batch
-    is trained in its own call).  Returns {client id: {epoch: {'loss', 'metrics'}}}."""
+    is trained in its own call).  `ready()` (optional) is called once the group's set-up — trainers, batch plans — is
+    done and its first step is about to be enqueued: the server lets the worker threads set up one group at a time, so
+    that the first group reaches the GPU after its own set-up and not after a third of everybody's (the set-up is
+    interpreter work under the GIL).  Returns {client id: {epoch: {'loss', 'metrics'}}}."""
     c0 = clients[0]
     dev = torch.device(c0.device)
     E = c0.args.E
@@ -173,6 +176,8 @@ def update_group(clients):
             if c.args.debug:
                 plan[c.id] = [b[:2] for b in plan[c.id]]
         rng_mode = getattr(c0.args, "droppath_rng", "fused")
+        if ready is not None:
+            ready()
         for e in range(E):
             feeds = {c.id: iter(c._staged.feed(plan[c.id][e])) for c in clients}
             seen = {c.id: 0 for c in clients}

@@ -18,6 +18,7 @@ Same constructor, attributes (`global_models`, `param_scope`, `clients`, `curr_l
 
 Client sampling, coefficient bookkeeping, lr decay and result logging are kept in Python, unchanged."""
 import concurrent.futures
+import threading
 import gc
 import json
 import logging
@@ -328,13 +329,24 @@ class FedavgServer(BaseServer):
             from ..client.fedavgclient import update_group as run
             dev = torch.device(group[0].device)
             stream = self._take_stream(dev)
+            # groups are set up one at a time (downloads, trainers, batch plans: interpreter work that three threads
+            # would only interleave under the GIL); the lock is handed on when the group's first step is enqueued
+            lock = self._prep_lock
+            lock.acquire()
+            held = [True]
+
+            def ready():
+                if held[0]:
+                    held[0] = False
+                    lock.release()
             try:
                 with torch.cuda.device(dev), torch.cuda.stream(stream):
                     for client in group:
                         prepare(client)
-                    res = run(group)
+                    res = run(group, ready=ready)
                     stream.synchronize()
             finally:
+                ready()
                 self._stream_pool[str(dev)].put(stream)
             out = []
             for client in group:
@@ -349,6 +361,7 @@ class FedavgServer(BaseServer):
                 out.append(({client.id: len(client.training_set)}, {client.id: res[client.id]}))
             return out
 
+        self.__dict__.setdefault("_prep_lock", threading.Lock())
         torch.cuda.synchronize(self.server_device)       # the global arenas the clients copy from are final
         local = [self.clients[i] for i in ids if self._owner.get(i, 0) == self.rank]
         groups = self._lockstep_groups(local)
