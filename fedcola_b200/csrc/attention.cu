@@ -29,6 +29,13 @@ using namespace sm100;
 
 constexpr int HD = 64;
 constexpr int TILE = 128 * 128;            // bytes of one 128-row x 128-byte swizzled tile (16 KB)
+#ifndef FC_ATTN_POLY_EXP2
+// which of every 4 column pairs of the forward's exp2 pass take the FMA-pipe polynomial (bit e) instead of MUFU.EX2.
+// Measured at B=112 N=197 H=6: 0 -> 32.8 us, 0x2 (25 %) -> 33.5, 0xA (50 %) -> 35.2, 0xE (75 %) -> 36.6: the pass is bound
+// by instruction issue and TMEM latency, not by the MUFU rate, so the default is off (profiles/experiments/README.md).
+#define FC_ATTN_POLY_EXP2 0x0
+#endif
+constexpr int kPolyExp2Mask = FC_ATTN_POLY_EXP2;
 #ifdef FC_ATTN_PROF
 __device__ long long g_attn_bprof[2][32 * 16];      // backward: [0] elementwise warp 0, [1] control lane; 32 chunks x 16 stamps
 #define BPROF(who, chunk, slot) do { if (blockIdx.x == 0 && (chunk) < 32) g_attn_bprof[who][(chunk) * 16 + (slot)] = clock64(); } while (0)
@@ -87,6 +94,25 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 of two scores on the FMA pipes (the forward's exp2 pass is MUFU-bound: 16 results per clock and SM):
+// x = v*c - max*c <= 0 clamped to -126; n = round(x) by the 1.5*2^23 trick, f = x - n in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (7.5e-5 relative, P is rounded to bf16 = 2e-3); 2^n goes into the exponent
+// field with one shift-add.  FFMA2 / FADD2: two columns per issue slot.
+__device__ __forceinline__ void ex2_pair_poly(float v0, float v1, float sc, float nmb, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(f2_fma(f2_pack(v0, v1), f2_all(sc), f2_all(nmb)), x0, x1);
+  const uint64_t x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t t = f2_add(x, f2_all(12582912.0f));
+  const uint64_t f = f2_add(x, f2_fma(t, f2_all(-1.0f), f2_all(12582912.0f)));        // x - (t - magic)
+  uint64_t q = f2_fma(f, f2_all(0.0551716685295105f), f2_all(0.2426111251115799f));
+  q = f2_fma(q, f, f2_all(0.6932609677314758f));
+  q = f2_fma(q, f, f2_all(0.9999280571937561f));
+  float q0, q1, t0, t1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 __device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // MN-major B operand made of ONE 64-wide block (V: rows = keys = K index, 128-byte rows of 64 head-dim values)
@@ -362,8 +388,13 @@ attn_fwd_tc_kernel(const __grid_constant__ FwdGroups G, int n_items, int items_p
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int i = 8 * j + 2 * e;
-                  const float p0 = ex2(fmaf(v[i], sc, nmb));
-                  const float p1 = ex2(fmaf(v[i + 1], sc, nmb));
+                  float p0, p1;
+                  if (kPolyExp2Mask & (1 << e)) {            // this pair on the FMA pipes, the others on the MUFU
+                    ex2_pair_poly(v[i], v[i + 1], sc, nmb, p0, p1);
+                  } else {
+                    p0 = ex2(fmaf(v[i], sc, nmb));
+                    p1 = ex2(fmaf(v[i + 1], sc, nmb));
+                  }
                   s0 += p0;
                   s1 += p1;
                   pk[e] = pack2(p0, p1);

@@ -261,4 +261,32 @@ __device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, uint32_t a, uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs: FFMA2 / FMUL2 / FADD2 do two fp32 lanes per issue slot (sm_100+).  The GELU epilogue is
+// bound by instruction issue (16 warps x ~20 instructions per element against a 2304-cycle main loop at K = 384),
+// so its arithmetic runs on pairs of adjacent accumulator columns (and part of the attention forward's exp2 does).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_all(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 }  // namespace sm100
