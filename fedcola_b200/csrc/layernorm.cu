@@ -420,11 +420,19 @@ extern "C" int fc_layernorm_fwd_grouped(int groups, const float* const* x, long 
                     y_f32 ? y_f32[g] : nullptr, mean ? mean[g] : nullptr, rstd ? rstd[g] : nullptr};
   }
   const int wpb = 8;
-  int grid = (rows + wpb - 1) / wpb;
-  const int cap = (fc_num_sms(device) * 8) / groups;      // rounded down: no CTA of a second wave
-  if (grid > cap) grid = cap;
+  const int want = (rows + wpb - 1) / wpb;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define FC_LN_FWD(NV) ln_fwd_kernel<NV><<<dim3(grid, groups), wpb * 32, 0, st>>>(S, x_row_stride, eps, rows, d)
+  // grid = the CTAs that are resident for this instantiation (48 registers at d = 384: 5 CTAs of 256 threads per SM),
+  // shared out over the groups and rounded down: no CTA of a second, partly filled wave
+#define FC_LN_FWD(NV)                                                                                          \
+  do {                                                                                                         \
+    int occ = 0;                                                                                               \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_fwd_kernel<NV>, wpb * 32, 0) != cudaSuccess || occ < 1) occ = 1; \
+    int cap = (fc_num_sms(device) * (occ < 8 ? occ : 8)) / groups;                                             \
+    if (cap < 1) cap = 1;                                                                                      \
+    const int grid = want < cap ? want : cap;                                                                  \
+    ln_fwd_kernel<NV><<<dim3(grid, groups), wpb * 32, 0, st>>>(S, x_row_stride, eps, rows, d);                 \
+  } while (0)
   const int nv = (d + 127) / 128;
   if (nv <= 1) FC_LN_FWD(1); else if (nv == 2) FC_LN_FWD(2); else if (nv == 3) FC_LN_FWD(3);
   else if (nv == 4) FC_LN_FWD(4); else if (nv <= 6) FC_LN_FWD(6); else FC_LN_FWD(8);

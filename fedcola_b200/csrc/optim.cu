@@ -420,6 +420,15 @@ int grid_for(int n_items, int device, int per_sm) {
   int g = fc_num_sms(device) * per_sm;
   return n_items < g ? n_items : g;
 }
+// Grid of a chunk-strided kernel = the CTAs that are actually RESIDENT (occupancy of this kernel, at most `max_per_sm`):
+// with 47 registers the optimizer kernels fit 5 CTAs of 256 threads per SM, so a grid of 8 per SM ran as a full wave
+// of 740 followed by a 60 %-filled one.
+template <typename K>
+int resident_grid(K kernel, int n_items, int device, int max_per_sm) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+  return grid_for(n_items, device, occ < max_per_sm ? occ : max_per_sm);
+}
 
 }  // namespace
 
@@ -434,7 +443,7 @@ extern "C" int fc_adamw_step(float* params, const float* grads, float* exp_avg, 
   FcDeviceGuard guard(device);
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  adamw_kernel<<<grid_for(n_chunks, device, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  adamw_kernel<<<resident_grid(adamw_kernel, n_chunks, device, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, reinterpret_cast<const Chunk*>(chunks), n_chunks, lr, beta1, beta2, eps,
       weight_decay, bc1, bc2_sqrt, max_norm > 0.f ? grad_sumsq : nullptr, max_norm);
   FC_LAUNCH_CHECK();
@@ -537,13 +546,13 @@ extern "C" int fc_opt_fused(float* params, float* grads, float* state0, float* s
   h.momentum = momentum; h.dampening = dampening; h.nesterov = nesterov; h.first_step = step == 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (n_chunks_a > 0) {
-    fused_opt_kernel<0><<<grid_for(n_chunks_a, device, 8), 256, 0, st>>>(
+    fused_opt_kernel<0><<<resident_grid(fused_opt_kernel<0>, n_chunks_a, device, 8), 256, 0, st>>>(
         params, grads, state0, state1, reinterpret_cast<__nv_bfloat16*>(operands_bf16),
         reinterpret_cast<const FChunk*>(chunks_a), n_chunks_a, reinterpret_cast<const FAuxLayer*>(aux_layers), counters, h);
     FC_LAUNCH_CHECK();
   }
   if (n_chunks_b > 0) {
-    fused_opt_kernel<1><<<grid_for(n_chunks_b, device, 8), 256, 0, st>>>(
+    fused_opt_kernel<1><<<resident_grid(fused_opt_kernel<1>, n_chunks_b, device, 8), 256, 0, st>>>(
         params, grads, state0, state1, reinterpret_cast<__nv_bfloat16*>(operands_bf16),
         reinterpret_cast<const FChunk*>(chunks_b), n_chunks_b, reinterpret_cast<const FAuxLayer*>(aux_layers), counters, h);
     FC_LAUNCH_CHECK();
